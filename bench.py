@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the ZNCC cost-volume hot path (forward + WTA + backward) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload kitti|cfg2|cfg3] [--impl b200|reference|reference-cuda]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic stereo pairs: forward cost volume + fused
+winner-take-all, then the backward camera gradient for an upstream gradient that is already on the device.
+Metric (BASELINE.json): Mpix*disp/s = 1e-6 * cost-volume cells / second, fwd+bwd, whole job over all N GPUs.
+
+Default workload ("kitti"): P pairs per GPU of KITTI size 1242x375, 192 disparities, 5x5 window (BASELINE.json
+configs[1]'s shape; at N = 8 and P = 8 it is configs[3], the batch of 64 pairs, batch-sharded).  Weak scaling: the
+per-GPU batch is fixed.  No data-path collective; the [B,H,W] results are gathered with NCCL inside the step when N > 1.
+
+Rank 0 prints ONE JSON line.  `value` is measured with inputs resident in HBM; `e2e` goes through the C-ABI
+host-buffer entry point (custma_host_step) with pinned host images in and host results out, copies inside the timed
+region.  `roofline` is for the dominant kernel group, timed live with CUDA events on the launching stream.
+`cpu_baseline` is the pure-PyTorch CPU restatement of the reference math (oracle/) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, D, k, default pairs per GPU, description)
+    "kitti": (375, 1242, 192, 5, 8, "KITTI-size pairs 1242x375, D=192, k=5 (BASELINE configs[1] shape; 8 pairs/GPU, "
+                                    "N=8 is configs[3]'s batch of 64)"),
+    "cfg2": (375, 1242, 192, 5, 1, "BASELINE configs[1]: one KITTI-size pair 1242x375, D=192, k=5"),
+    "cfg3": (1988, 2880, 256, 5, 1, "BASELINE configs[2]: one Middlebury-full-size pair 2880x1988, D=256, k=5"),
+    "cfg1": (240, 320, 64, 5, 1, "BASELINE configs[0]: one 320x240 pair, D=64, k=5"),
+}
+METRIC = "Mpix*disp/s fwd+bwd (cost-volume cells per second, forward+WTA+backward)"
+UNIT = "Mpix*disp/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML, nvidia-smi fallback)."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            handle = None
+            if uuid:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    u = pynvml.nvmlDeviceGetUUID(h)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u:
+                        handle = h
+                        break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml = (pynvml, handle)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _reasons(self, pynvml, handle):
+        try:
+            get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(handle))
+        except Exception:
+            return
+        names = {
+            0x0000000000000004: "sw_power_cap", 0x0000000000000008: "hw_slowdown",
+            0x0000000000000020: "sw_thermal_slowdown", 0x0000000000000040: "hw_thermal_slowdown",
+            0x0000000000000080: "hw_power_brake_slowdown", 0x0000000000000002: "applications_clocks_setting",
+            0x0000000000000010: "sync_boost", 0x0000000000000100: "display_clock_setting",
+        }
+        for bit, name in names.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        pynvml, handle = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                self._reasons(pynvml, handle)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        self._open()
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(2.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def cpu_torch_port_rate(H, W, D, k, budget_s=12.0, max_rows=None, threads=None):
+    """fwd + WTA + bwd of the pure-PyTorch CPU restatement (oracle/zncc_oracle.py) on a bounded sample:
+    a band of image rows of ONE pair of the workload's shape.  Returns (Mcells/s, description, threads)."""
+    import torch
+    from oracle import zncc_oracle as zo
+    if threads:
+        torch.set_num_threads(threads)
+    rows = min(H, max_rows or H)
+    gen = torch.Generator().manual_seed(0)
+    cam = torch.rand(rows, W, generator=gen)
+    proj = torch.rand(rows, W, generator=gen)
+    g = torch.randn(rows, W, W, generator=torch.Generator().manual_seed(1))
+    cells = rows * W * W
+    zo.cpu_baseline_step_full(cam[:8], proj[:8], g[:8], k)  # warm
+    best, n, t_total = None, 0, 0.0
+    while n < 1 or (t_total < budget_s and n < 6):
+        t0 = time.perf_counter()
+        zo.cpu_baseline_step_full(cam, proj, g, k)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        t_total += dt
+        n += 1
+    return cells / best / 1e6, (f"1 pair, {rows} of {H} image rows, reference-shaped [rows,{W},{W}] volume "
+                                f"(verify.py's bmm form, D ignored as in the reference), k={k}, fp32 torch CPU, "
+                                f"fwd+WTA+bwd, best of {n}"), torch.get_num_threads()
+
+
+def run_reference_cpu(args):
+    """--impl reference: the reference's math on the host cores (the reference has no CPU kernel and its CUDA
+    extension is not a CPU implementation, so this is the oracle port: kind = "port")."""
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    H, W, D, k, _, desc = WORKLOADS[args.workload]
+    import torch
+    from oracle import zncc_oracle as zo
+    rows = min(H, args.ref_rows)
+    gen = torch.Generator().manual_seed(0)
+    cam = torch.rand(rows, W, generator=gen)
+    proj = torch.rand(rows, W, generator=gen)
+    g = torch.randn(rows, W, W, generator=torch.Generator().manual_seed(1))
+    cells = rows * W * W
+    for _ in range(args.warmup):
+        zo.cpu_baseline_step_full(cam, proj, g, k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        zo.cpu_baseline_step_full(cam, proj, g, k)
+    dt = time.perf_counter() - t0
+    value = cells * args.steps / dt / 1e6
+    sample = (f"each step = 1 pair, {rows} of {H} image rows, reference-shaped [rows,{W},{W}] volume (verify.py's bmm "
+              f"form; the reference ignores D), k={k}, fwd+WTA+bwd, fp32 torch on CPU")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "H": H, "W": W, "D": D, "kernel_size": k, "sample_rows": rows},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample, "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference ships no CPU kernel (CHECK_CUDA, custma/include/stereo_matching.hpp:20); this arm is "
+                "the pure-PyTorch CPU restatement of examples/verify.py:91-123 that BASELINE.json's north_star names",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda(args):
+    """--impl reference-cuda: the UNMODIFIED reference CUDA extension from baseline/_ref on this GPU (full [H,W,W]
+    volume, since the reference ignores D).  Extra information, not part of the driver contract."""
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    H, W, D, k, _, desc = WORKLOADS[args.workload]
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import torch
+        import custma as ref_custma
+        assert "baseline" in os.path.abspath(ref_custma.__file__)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "reference-cuda", "unavailable": f"{type(e).__name__}: {e}"[:200]}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    gen = torch.Generator().manual_seed(0)
+    cam = torch.rand(H, W, generator=gen).cuda().requires_grad_(True)
+    proj = torch.rand(H, W, generator=gen).cuda()
+    cells = H * W * W
+    if cells >= 2 ** 31:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "H*W*W overflows the reference's int32 element count"}))
+        return
+    g = torch.randn(H, W, W, device="cuda")
+
+    def step():
+        cam.grad = None
+        cv = ref_custma.stereo_matching(cam, proj, D, k)
+        cv.backward(g)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "reference-cuda", "metric": METRIC, "value": cells / ms / 1e3, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": desc + " - reference computes the full [H,W,W] volume (D ignored)",
+                                 "cells_per_step": cells}}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from custereomatching_b200 import binding
+
+    rank, local, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    binding.load()                                                   # fail loudly if the extension is missing
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    H, W, D, k, default_pairs, desc = WORKLOADS[args.workload]
+    P = args.pairs_per_gpu or default_pairs
+    flags = binding.FLAG_DIRECT if args.direct else 0
+    pix = H * W
+    cells_rank = P * pix * D
+    cells_job = cells_rank * world
+
+    # ---- synthetic inputs: host (pinned) images, device-resident upstream gradient -------------------------------
+    gen = torch.Generator().manual_seed(1000 + rank)
+    h_cam = torch.rand(P, H, W, generator=gen).pin_memory()
+    h_proj = torch.rand(P, H, W, generator=gen).pin_memory()
+    cam = h_cam.to(device)
+    proj = h_proj.to(device)
+    ggen = torch.Generator(device=device).manual_seed(1)
+    grad_in = torch.randn(P, H, W, D, device=device, generator=ggen)
+    cost = torch.empty(P, H, W, D, device=device)
+    best = torch.empty(P, H, W, device=device)
+    disp = torch.empty(P, H, W, dtype=torch.int32, device=device)
+    cam_grad = torch.empty(P, H, W, device=device)
+    ws_bytes = max(binding.forward_workspace_bytes(P, H, W, D, k, flags),
+                   binding.backward_workspace_bytes(P, H, W, D, k, flags))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    if world > 1:
+        gather_f = torch.empty(2, world * P, H, W, device=device)           # best, camera_grad
+        gather_i = torch.empty(world * P, H, W, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+    sptr = stream.cuda_stream
+
+    def fwd():
+        binding.forward(cam.data_ptr(), proj.data_ptr(), cost.data_ptr(), best.data_ptr(), disp.data_ptr(),
+                        P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
+
+    def bwd():
+        binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(),
+                         P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
+
+    def gather():
+        if world > 1:   # results only: 3 * P*H*W*4 bytes per rank; the volume never leaves the GPU
+            dist.all_gather_into_tensor(gather_f[0], best)
+            dist.all_gather_into_tensor(gather_i, disp)
+            dist.all_gather_into_tensor(gather_f[1], cam_grad)
+
+    def step():
+        fwd()
+        bwd()
+        gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region 1: whole step, device-resident inputs ------------------------------------------------------
+    K = args.steps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    launches0 = binding.launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev[0].record(stream)
+        for _ in range(K):
+            step()
+        ev[1].record(stream)
+        barrier()
+    launches = (binding.launch_count() - launches0) // K
+    ms_total = ev[0].elapsed_time(ev[1])
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+
+    # ---- timed region 2: forward and backward kernel groups separately (roofline of the dominant one) ------------
+    Kk = min(K, 20)
+    e_f = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    e_b = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    barrier()
+    for i in range(Kk):
+        e_f[i][0].record(stream); fwd(); e_f[i][1].record(stream)
+        e_b[i][0].record(stream); bwd(); e_b[i][1].record(stream)
+    barrier()
+    ms_f = sum(a.elapsed_time(b) for a, b in e_f) / Kk
+    ms_b = sum(a.elapsed_time(b) for a, b in e_b) / Kk
+    peak, peak_src = measured_peak_gbs()
+    bytes_f = 4 * cells_rank + 8 * P * pix + 8 * P * pix      # write cost once; read 2 images; write best + disparity
+    bytes_b = 4 * cells_rank + 8 * P * pix + 4 * P * pix      # read upstream gradient once; read 2 images; write grad
+    roof_f = {"kernel": "custma_forward (window stats + cost volume + WTA)", "bound": "hbm",
+              "achieved": bytes_f / ms_f / 1e6, "peak": peak, "unit": "GB/s", "frac": bytes_f / ms_f / 1e6 / peak,
+              "traffic": None, "ms_per_launch": ms_f, "algorithmic_bytes": bytes_f}
+    roof_b = {"kernel": "custma_backward (window stats + camera gradient)", "bound": "hbm",
+              "achieved": bytes_b / ms_b / 1e6, "peak": peak, "unit": "GB/s", "frac": bytes_b / ms_b / 1e6 / peak,
+              "traffic": None, "ms_per_launch": ms_b, "algorithmic_bytes": bytes_b}
+    dominant = dict(roof_b if ms_b >= ms_f else roof_f)
+    dominant["peak_source"] = peak_src
+    dominant["step"] = {"fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_frac": roof_f["frac"], "bwd_frac": roof_b["frac"],
+                        "fwd_bwd_frac": (bytes_f + bytes_b) / (ms_f + ms_b) / 1e6 / peak}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the last ncu capture
+    if os.path.exists(traffic_path):
+        try:
+            tr = json.load(open(traffic_path))
+            key = "backward" if ms_b >= ms_f else "forward"
+            if tr.get("workload") == args.workload and tr.get("pairs_per_gpu") == P:
+                dominant["traffic"] = tr.get(key)
+        except Exception:
+            pass
+
+    # ---- timed region 3: end to end through the C-ABI host entry point -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_best = torch.empty(P, H, W).pin_memory()
+        h_disp = torch.empty(P, H, W, dtype=torch.int32).pin_memory()
+        h_grad = torch.empty(P, H, W).pin_memory()
+
+        def host_step():
+            binding.host_step(h_cam.data_ptr(), h_proj.data_ptr(), h_best.data_ptr(), h_disp.data_ptr(),
+                              h_grad.data_ptr(), cost.data_ptr(), grad_in.data_ptr(), P, H, W, D, k, flags)
+
+        for _ in range(3):
+            host_step()
+        Ke = max(3, min(K, 20))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            host_step()                                              # synchronous: returns with results on the host
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        e2e = {"value": cells_job * Ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * P * pix * 4,
+               "d2h_bytes_per_step": 3 * P * pix * 4, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
+               "api": "custma_host_step (include/custma_b200.h): pinned host images in, host best/disparity/"
+                      "camera_grad out; upstream gradient produced on the device"}
+        # parity of the two paths on this very data (cheap sanity, outside the timed regions)
+        same = bool(torch.equal(h_best.to(device), best) and torch.equal(h_grad.to(device), cam_grad))
+        e2e["matches_device_path"] = same
+        binding.host_release()
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sample, threads = cpu_torch_port_rate(H, W, D, k, max_rows=args.ref_rows)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+               "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": cells_job / ms_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "H": H, "W": W, "D": D, "kernel_size": k, "pairs_per_gpu": P,
+                       "global_pairs": P * world, "cells_per_step": cells_job,
+                       "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"inputs larger than L2: {4 * cells_rank / 1e6:.0f} MB volume written and "
+                             f"{4 * cells_rank / 1e6:.0f} MB gradient read per step per GPU (L2 = 126 MB)",
+                       "kernels": "direct two-pass" if args.direct else "default (sliding-window where available)"},
+            "roofline": dominant, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs-per-gpu", type=int, default=0)
+    ap.add_argument("--direct", action="store_true", help="force the direct two-pass kernels (CUSTMA_FLAG_DIRECT)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-rows", type=int, default=48, help="image rows of one pair in the CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_cpu(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""custereomatching_b200 - B200-native (sm_100a only) ZNCC cost-volume hot path of lzhnb/CuStereoMatching.
+
+  csrc/         hand-written CUDA kernels + the C ABI (include/custma_b200.h) -> libcustma_b200.so
+  build.py      in-tree nvcc build of that library
+  binding.py    ctypes binding of the C ABI (no torch types cross it)
+  functional.py torch-facing host layer: allocation, checks, autograd
+  sharding.py   batch / row-band partitioning across the GPUs of one box (torch.distributed)
+
+The drop-in Python surface of the reference lives in the top-level `custma` package.
+"""
+from . import binding
+from .functional import (FLAG_DIRECT, INVALID_COST, backward, confidence_mask, cost_volume, cost_volume_and_wta,
+                         forward, wta)
+
+__all__ = ["binding", "forward", "backward", "cost_volume", "wta", "cost_volume_and_wta", "confidence_mask",
+           "FLAG_DIRECT", "INVALID_COST"]

@@ -1,0 +1,131 @@
+"""ctypes binding of libcustma_b200.so (the C ABI declared in include/custma_b200.h).
+
+This is the only place that touches the shared library.  There is NO fallback: if the library is missing or a call
+fails, a RuntimeError is raised (the reference raises RuntimeError through TORCH_CHECK,
+custma/include/stereo_matching.hpp:20-25).  PyTorch is used for device memory and streams only; every pointer
+crossing the boundary is a plain address.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libcustma_b200.so")
+
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_WORKSPACE = 2
+ERR_CUDA = 3
+ERR_UNSUPPORTED = 4
+FLAG_DIRECT = 1
+INVALID_COST = -2.0
+ABI_VERSION = 1
+
+# every symbol include/custma_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = (
+    "custma_abi_version",
+    "custma_last_error",
+    "custma_launch_count",
+    "custma_forward_workspace_bytes",
+    "custma_backward_workspace_bytes",
+    "custma_forward",
+    "custma_backward",
+    "custma_host_step",
+    "custma_host_release",
+)
+
+_lib = None
+_lock = threading.Lock()
+
+_i32 = ctypes.c_int32
+_u32 = ctypes.c_uint32
+_ptr = ctypes.c_void_p
+_size = ctypes.c_size_t
+
+
+def _declare(lib):
+    lib.custma_abi_version.restype = ctypes.c_int
+    lib.custma_abi_version.argtypes = []
+    lib.custma_last_error.restype = ctypes.c_char_p
+    lib.custma_last_error.argtypes = []
+    lib.custma_launch_count.restype = ctypes.c_uint64
+    lib.custma_launch_count.argtypes = []
+    for name in ("custma_forward_workspace_bytes", "custma_backward_workspace_bytes"):
+        fn = getattr(lib, name)
+        fn.restype = _size
+        fn.argtypes = [_i32, _i32, _i32, _i32, _i32, _u32]
+    lib.custma_forward.restype = ctypes.c_int
+    lib.custma_forward.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_backward.restype = ctypes.c_int
+    lib.custma_backward.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_host_step.restype = ctypes.c_int
+    lib.custma_host_step.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32]
+    lib.custma_host_release.restype = ctypes.c_int
+    lib.custma_host_release.argtypes = []
+
+
+def load():
+    """Returns the loaded library; raises RuntimeError if it has not been built (no CPU or eager fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python setup.py build_ext --inplace` or "
+                    "`python -m custereomatching_b200.build`; custma has no CPU or eager fallback")
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            got = lib.custma_abi_version()
+            if got != ABI_VERSION:
+                raise RuntimeError(f"libcustma_b200.so has ABI version {got}, this binding expects {ABI_VERSION}")
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load().custma_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def launch_count() -> int:
+    return int(load().custma_launch_count())
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def forward_workspace_bytes(B, H, W, D, k, flags=0) -> int:
+    return int(load().custma_forward_workspace_bytes(B, H, W, D, k, flags))
+
+
+def backward_workspace_bytes(B, H, W, D, k, flags=0) -> int:
+    return int(load().custma_backward_workspace_bytes(B, H, W, D, k, flags))
+
+
+def forward(camera_ptr, projector_ptr, cost_ptr, best_ptr, index_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    rc = load().custma_forward(camera_ptr, projector_ptr, cost_ptr or None, best_ptr or None, index_ptr or None,
+                               B, H, W, D, k, flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_forward")
+
+
+def backward(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    rc = load().custma_backward(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, flags,
+                                ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_backward")
+
+
+def host_step(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev,
+              B, H, W, D, k, flags=0):
+    rc = load().custma_host_step(h_camera, h_projector, h_best, h_index, h_camera_grad or None,
+                                 cost_volume_dev or None, cost_volume_grad_dev or None, B, H, W, D, k, flags)
+    check(rc, "custma_host_step")
+
+
+def host_release():
+    check(load().custma_host_release(), "custma_host_release")

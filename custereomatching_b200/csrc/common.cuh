@@ -1,0 +1,71 @@
+// Shared definitions for the custma_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "custma_b200.h"
+
+namespace custma {
+
+constexpr float kEps = CUSTMA_EPSILON;          // reference: custma/src/stereo_matching_kernel.cu:4
+constexpr float kInvalid = CUSTMA_INVALID_COST;
+
+// One problem instance.  C is the length of the volume's last axis: W in full (reference-shaped) mode, D when banded.
+struct Problem {
+    int32_t B, H, W, D, C, k, r;  // r = k / 2 (window offsets i - r, reference kernel.cu:44-46)
+    int32_t banded;               // 0: last axis = projector column d ; 1: last axis = disparity s, d = w - s
+    __host__ __device__ int64_t pixels() const { return (int64_t)B * H * W; }
+    __host__ __device__ int64_t cells() const { return (int64_t)B * H * W * C; }
+};
+
+// Bounds-checked read, 0 outside the image: restates query_ij (reference kernel.cu:6-12) for one [H,W] plane.
+__device__ __forceinline__ float query_ij(const float *__restrict__ img, int H, int W, int i, int j) {
+    return (i < 0 || i >= H || j < 0 || j >= W) ? 0.f : __ldg(img + (int64_t)i * W + j);
+}
+
+// thread-local error message storage (custma_api.cu)
+int set_error(int code, const char *fmt, ...);
+// process-wide count of kernels this library has launched (custma_launch_count)
+void note_launch();
+
+#define CUSTMA_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return custma::set_error(CUSTMA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                     __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define CUSTMA_LAUNCH_CHECK(name)                                                                      \
+    do {                                                                                               \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return custma::set_error(CUSTMA_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+        custma::note_launch();                                                                         \
+    } while (0)
+
+inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// ---- launchers implemented in the .cu files -------------------------------------------------------------------
+// per-pixel window statistics of one [B,H,W] image in the reference's own arithmetic order
+int launch_window_stats(const float *img, int B, int H, int W, int k, float *mean, float *e2, cudaStream_t stream);
+
+// direct (two-pass, reference arithmetic order) kernels: any k <= CUSTMA_MAX_KERNEL_SIZE, full or banded
+int launch_direct_forward(const Problem &p, const float *cam, const float *proj, const float *cmean,
+                          const float *cex2, const float *pmean, const float *pey2, float *cost, float *best,
+                          int32_t *index, cudaStream_t stream);
+int launch_direct_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
+                           const float *cmean, const float *cex2, const float *pmean, const float *pey2,
+                           float *patch_grad /* [B,H,W,k*k] workspace */, float *camera_grad, cudaStream_t stream);
+
+// sliding-window kernels (sliding_forward.cu / sliding_backward.cu); return CUSTMA_ERR_UNSUPPORTED if the
+// (k, mode) combination has no instantiation, in which case the caller falls back to the direct kernels.
+bool sliding_supported(const Problem &p);
+size_t sliding_forward_workspace_bytes(const Problem &p);
+size_t sliding_backward_workspace_bytes(const Problem &p);
+int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
+                           int32_t *index, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
+                            float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace custma

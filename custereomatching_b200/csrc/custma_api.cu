@@ -1,0 +1,139 @@
+// C-ABI entry points of libcustma_b200.so (see include/custma_b200.h): argument validation, workspace layout,
+// dispatch between the sliding-window kernels and the direct two-pass kernels.
+#include <stdarg.h>
+#include <atomic>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace custma {
+
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int check_device() {
+    static thread_local int checked_device = -1;
+    int dev = 0;
+    CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev == checked_device) return CUSTMA_OK;
+    int major = 0;
+    CUSTMA_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        return set_error(CUSTMA_ERR_UNSUPPORTED,
+                         "device %d has compute capability %d.x; this library carries sm_100a code only", dev, major);
+    checked_device = dev;
+    return CUSTMA_OK;
+}
+
+static int make_problem(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, Problem *p) {
+    if (B <= 0 || H <= 0 || W <= 0) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "B, H, W must be positive (got %d, %d, %d)", B, H, W);
+    if (D < 0) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "D must be >= 0 (0 selects the reference-shaped [H,W,W] volume), got %d", D);
+    if (k < 1 || k > CUSTMA_MAX_KERNEL_SIZE)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "kernel_size must be in [1, %d], got %d", CUSTMA_MAX_KERNEL_SIZE, k);
+    p->B = B; p->H = H; p->W = W; p->D = D; p->k = k; p->r = k / 2;
+    p->banded = D > 0;
+    p->C = D > 0 ? D : W;
+    return CUSTMA_OK;
+}
+
+// workspace layout: [cam mean][cam e2][proj mean][proj e2][path-specific...]
+struct StatsPtrs { float *cmean, *cex2, *pmean, *pey2; char *rest; size_t rest_bytes; };
+
+static size_t stats_bytes(const Problem &p) { return 4 * align256((size_t)p.pixels() * sizeof(float)); }
+
+static int carve_stats(const Problem &p, void *ws, size_t ws_bytes, size_t need, StatsPtrs *s) {
+    if (!ws || ws_bytes < need)
+        return set_error(CUSTMA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, ws ? ws_bytes : (size_t)0);
+    if (((uintptr_t)ws & 255) != 0) return set_error(CUSTMA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    const size_t one = align256((size_t)p.pixels() * sizeof(float));
+    char *base = (char *)ws;
+    s->cmean = (float *)base; s->cex2 = (float *)(base + one);
+    s->pmean = (float *)(base + 2 * one); s->pey2 = (float *)(base + 3 * one);
+    s->rest = base + 4 * one; s->rest_bytes = ws_bytes - 4 * one;
+    return CUSTMA_OK;
+}
+
+static bool use_sliding(const Problem &p, uint32_t flags) { return !(flags & CUSTMA_FLAG_DIRECT) && sliding_supported(p); }
+
+static size_t forward_ws(const Problem &p, uint32_t flags) {
+    return stats_bytes(p) + (use_sliding(p, flags) ? sliding_forward_workspace_bytes(p) : 0);
+}
+static size_t backward_ws(const Problem &p, uint32_t flags) {
+    if (use_sliding(p, flags)) return stats_bytes(p) + sliding_backward_workspace_bytes(p);
+    return stats_bytes(p) + align256((size_t)p.pixels() * p.k * p.k * sizeof(float));
+}
+
+}  // namespace custma
+
+using namespace custma;
+
+extern "C" {
+
+int custma_abi_version(void) { return CUSTMA_ABI_VERSION; }
+const char *custma_last_error(void) { return g_error; }
+uint64_t custma_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t custma_forward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    Problem p;
+    if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
+    return forward_ws(p, flags);
+}
+
+size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    Problem p;
+    if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
+    return backward_ws(p, flags);
+}
+
+int custma_forward(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
+                   int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
+                   size_t workspace_bytes, void *stream_) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if (!camera || !projector) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera and projector must not be NULL");
+    if (!cost_volume && !best) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "no output requested (cost_volume and best are both NULL)");
+    if ((best == nullptr) != (index == nullptr)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "best and index must be given together");
+    if ((rc = check_device())) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    StatsPtrs s;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, forward_ws(p, flags), &s))) return rc;
+    if (use_sliding(p, flags))
+        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, workspace, workspace_bytes, stream);
+    if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
+    if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+    return launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream);
+}
+
+int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
+                    int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
+                    size_t workspace_bytes, void *stream_) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if (!cost_volume_grad || !camera || !projector || !camera_grad)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "cost_volume_grad, camera, projector and camera_grad must not be NULL");
+    if ((rc = check_device())) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    StatsPtrs s;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, backward_ws(p, flags), &s))) return rc;
+    if (use_sliding(p, flags))
+        return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, workspace, workspace_bytes, stream);
+    if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
+    if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+    return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,
+                                  (float *)s.rest, camera_grad, stream);
+}
+
+}  // extern "C"

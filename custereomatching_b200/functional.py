@@ -1,0 +1,166 @@
+"""Torch-facing host layer over the C ABI: allocation, input checks, autograd glue.
+
+Mirrors the reference's host entry points for the hot path and nothing else:
+  stereo_matching_forward   custma/src/stereo_matching.cpp:16-42  (CHECK_INPUT on both images, callee allocates)
+  stereo_matching_backward  custma/src/stereo_matching.cpp:45-73  (CHECK_INPUT on the gradient only, H/W from it)
+  _StereoMatching           custma/stereo_matching_wrapper.py:7-35 (camera-only gradient)
+and adds the banded / batched / fused-WTA entry points BASELINE.json's configs name.  Differences from the
+reference that a caller can observe, all deliberate:
+  * kernels run on torch's CURRENT stream of the inputs' device (the reference uses legacy stream 0),
+  * outputs are written exactly once (no torch::zeros pre-fill), sizes are 64-bit,
+  * the backward is deterministic (no atomics),
+  * shape / dtype mismatches raise RuntimeError instead of being undefined behaviour (the reference's assert at
+    stereo_matching.cpp:28 is compiled out).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import binding
+
+INVALID_COST = binding.INVALID_COST
+FLAG_DIRECT = binding.FLAG_DIRECT
+
+
+def _check_input(x: torch.Tensor, name: str) -> None:
+    # same messages as CHECK_CUDA / CHECK_CONTIGUOUS (custma/include/stereo_matching.hpp:20-25)
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(x).__name__}")
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if x.dtype != torch.float32:
+        # the reference's data_ptr<float>() throws for any other dtype (stereo_matching_kernel.cu:209-212)
+        raise RuntimeError(f"{name} must be a float32 tensor, got {x.dtype}")
+
+
+def _shape_bhw(camera: torch.Tensor, projector: torch.Tensor) -> Tuple[int, int, int, bool]:
+    if camera.dim() not in (2, 3):
+        raise RuntimeError(f"camera must be [H, W] or [B, H, W], got {tuple(camera.shape)}")
+    if camera.shape != projector.shape:
+        raise RuntimeError(f"camera {tuple(camera.shape)} and projector {tuple(projector.shape)} must have the same shape")
+    if camera.device != projector.device:
+        raise RuntimeError("camera and projector must be on the same device")
+    batched = camera.dim() == 3
+    B = camera.shape[0] if batched else 1
+    H, W = camera.shape[-2], camera.shape[-1]
+    if B == 0 or H == 0 or W == 0:
+        raise RuntimeError(f"empty input {tuple(camera.shape)}")
+    return B, H, W, batched
+
+
+def _workspace(nbytes: int, device) -> Tuple[Optional[torch.Tensor], int]:
+    if nbytes == 0:
+        return None, 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)  # caching allocator: 512-byte aligned
+    return ws, ws.data_ptr()
+
+
+def forward(camera: torch.Tensor, projector: torch.Tensor, D: int = 0, kernel_size: int = 5, *,
+            want_cost: bool = True, want_wta: bool = False, flags: int = 0):
+    """ZNCC cost volume and / or winner-take-all.
+
+    camera, projector: float32 CUDA, [H,W] or [B,H,W].  D == 0: reference-shaped volume [...,H,W,W] whose last axis
+    is the projector column; D > 0: banded volume [...,H,W,D] whose last axis is the disparity s (projector column
+    w - s; cells with w - s < 0 hold INVALID_COST).  Returns (cost | None, best | None, index | None); index is
+    int32: first maximal projector column (D == 0) or the disparity of it (D > 0).
+    """
+    _check_input(camera, "camera")
+    _check_input(projector, "projector")
+    B, H, W, batched = _shape_bhw(camera, projector)
+    if not (want_cost or want_wta):
+        raise RuntimeError("nothing to compute: want_cost and want_wta are both False")
+    D = int(D)
+    k = int(kernel_size)
+    C = D if D > 0 else W
+    lead = (B,) if batched else ()
+    with torch.cuda.device(camera.device):
+        cost = torch.empty(lead + (H, W, C), dtype=torch.float32, device=camera.device) if want_cost else None
+        best = torch.empty(lead + (H, W), dtype=torch.float32, device=camera.device) if want_wta else None
+        index = torch.empty(lead + (H, W), dtype=torch.int32, device=camera.device) if want_wta else None
+        nbytes = binding.forward_workspace_bytes(B, H, W, D, k, flags)
+        if nbytes == 0:  # the query validates the arguments; every valid problem needs a non-empty workspace
+            binding.check(binding.ERR_INVALID_ARGUMENT, "custma_forward_workspace_bytes")
+        ws, ws_ptr = _workspace(nbytes, camera.device)
+        stream = torch.cuda.current_stream(camera.device).cuda_stream
+        binding.forward(camera.data_ptr(), projector.data_ptr(),
+                        cost.data_ptr() if cost is not None else 0,
+                        best.data_ptr() if best is not None else 0,
+                        index.data_ptr() if index is not None else 0,
+                        B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream(camera.device))
+    return cost, best, index
+
+
+def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: torch.Tensor, kernel_size: int,
+             D: int = 0, *, flags: int = 0) -> torch.Tensor:
+    """Gradient of sum(cost * cost_volume_grad) with respect to the camera image; same leading shape as camera."""
+    _check_input(cost_volume_grad, "cost_volume_grad")
+    _check_input(camera, "camera")
+    _check_input(projector, "projector")
+    B, H, W, batched = _shape_bhw(camera, projector)
+    D = int(D)
+    C = D if D > 0 else W
+    lead = (B,) if batched else ()
+    if tuple(cost_volume_grad.shape) != lead + (H, W, C):
+        raise RuntimeError(f"cost_volume_grad must have shape {lead + (H, W, C)}, got {tuple(cost_volume_grad.shape)}")
+    if cost_volume_grad.device != camera.device:
+        raise RuntimeError("cost_volume_grad must be on the images' device")
+    k = int(kernel_size)
+    with torch.cuda.device(camera.device):
+        camera_grad = torch.empty_like(camera)
+        nbytes = binding.backward_workspace_bytes(B, H, W, D, k, flags)
+        if nbytes == 0:
+            binding.check(binding.ERR_INVALID_ARGUMENT, "custma_backward_workspace_bytes")
+        ws, ws_ptr = _workspace(nbytes, camera.device)
+        stream = torch.cuda.current_stream(camera.device).cuda_stream
+        binding.backward(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
+                         camera_grad.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream(camera.device))
+    return camera_grad
+
+
+class _CostVolume(torch.autograd.Function):
+    """Differentiable cost volume, banded or full, batched or not; gradient w.r.t. the camera image only."""
+
+    @staticmethod
+    def forward(ctx, camera, projector, D, kernel_size, flags):
+        ctx.save_for_backward(camera, projector)
+        ctx.D, ctx.kernel_size, ctx.flags = int(D), int(kernel_size), int(flags)
+        cost, _, _ = forward(camera, projector, D, kernel_size, want_cost=True, want_wta=False, flags=flags)
+        return cost
+
+    @staticmethod
+    def backward(ctx, cost_volume_grad):
+        camera, projector = ctx.saved_tensors
+        g = backward(cost_volume_grad.contiguous(), camera, projector, ctx.kernel_size, ctx.D, flags=ctx.flags)
+        return g, None, None, None, None
+
+
+def cost_volume(camera, projector, D: int = 0, kernel_size: int = 5, flags: int = 0) -> torch.Tensor:
+    """Differentiable (camera only) ZNCC volume: [...,H,W,W] for D == 0, banded [...,H,W,D] for D > 0."""
+    return _CostVolume.apply(camera, projector, D, kernel_size, flags)
+
+
+def wta(camera, projector, D: int = 0, kernel_size: int = 5, flags: int = 0):
+    """Fused forward + winner-take-all without materialising the volume: (best fp32, index int32).
+
+    Equals torch.max(cost_volume, -1) of examples/verify.py:72 (first maximal projector column); for D > 0 the
+    index is the disparity w - column (examples/test.py:83)."""
+    _, best, index = forward(camera, projector, D, kernel_size, want_cost=False, want_wta=True, flags=flags)
+    return best, index
+
+
+def cost_volume_and_wta(camera, projector, D: int = 0, kernel_size: int = 5, flags: int = 0):
+    """(cost, best, index) from one pass over the volume (not differentiable; use cost_volume for autograd)."""
+    return forward(camera, projector, D, kernel_size, want_cost=True, want_wta=True, flags=flags)
+
+
+def confidence_mask(best: torch.Tensor, threshold: float = 0.6) -> torch.Tensor:
+    """examples/verify.py:74: 1 where the best ZNCC exceeds the threshold, else 0 (same dtype as best)."""
+    return (best > threshold).to(best.dtype)

@@ -1,0 +1,67 @@
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def golden_small_names():
+    man = json.load(open(os.path.join(GOLDEN_DIR, "manifest.json")))
+    return [c["name"] for c in man["cases"]]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def golden_manifest():
+    return json.load(open(os.path.join(GOLDEN_DIR, "manifest.json")))
+
+
+# Tolerances (BASELINE.json north_star "within 1e-5 relative (fp32)"):
+#   costs     |new - ref| <= COST_TOL * max(1, |ref|)        (|cost| <= 1, so this is 1e-5 of the cost scale)
+#   gradients |new - ref| <= GRAD_TOL * max|ref grad|
+COST_TOL = 1e-5
+GRAD_TOL = 1e-5
+
+
+def assert_cost_close(new, ref, tol=COST_TOL, what="cost"):
+    new = np.asarray(new, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert new.shape == ref.shape, (new.shape, ref.shape)
+    err = np.abs(new - ref) / np.maximum(1.0, np.abs(ref))
+    assert np.isfinite(new).all(), f"{what}: non-finite values"
+    assert err.max() <= tol, f"{what}: max scaled error {err.max():.3e} > {tol:.1e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def assert_grad_close(new, ref, tol=GRAD_TOL, what="grad", scale=None):
+    new = np.asarray(new, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert new.shape == ref.shape, (new.shape, ref.shape)
+    scale = float(np.abs(ref).max()) if scale is None else scale
+    scale = max(scale, 1e-30)
+    err = np.abs(new - ref).max() / scale
+    assert np.isfinite(new).all(), f"{what}: non-finite values"
+    assert err <= tol, f"{what}: max error {err:.3e} of the gradient scale {scale:.3e} > {tol:.1e}"

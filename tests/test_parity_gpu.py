@@ -1,0 +1,313 @@
+"""GPU parity tests: the CUDA path (through the C ABI: custma -> custereomatching_b200.binding -> libcustma_b200.so)
+against the golden vectors of the reference extension and against the CPU oracle on the same seeded inputs.
+
+Tolerances (conftest.py): costs |new-ref| <= 1e-5 * max(1,|ref|); gradients |new-ref| <= 1e-5 * max|ref grad|;
+WTA indices bit-exact wherever the best cost beats the runner-up by more than 1e-5 (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+import custma
+import custereomatching_b200 as cb
+from conftest import (COST_TOL, GRAD_TOL, assert_cost_close, assert_grad_close, golden_manifest, golden_small_names,
+                      load_golden)
+from oracle import ref_port
+from oracle import zncc_oracle as zo
+
+pytestmark = pytest.mark.gpu
+SMALL = golden_small_names()
+FLAGS = [0, cb.FLAG_DIRECT]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_pair(H, W, seed, B=None):
+    rng = np.random.RandomState(seed)
+    shape = (H, W) if B is None else (B, H, W)
+    return rng.rand(*shape).astype(np.float32), rng.rand(*shape).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference-shaped [H,W,W] drop-in path against the reference extension's own outputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_drop_in_forward_backward_vs_reference_golden(name):
+    g = load_golden(name)
+    k = int(g["kernel_size"])
+    cam = dev(g["camera"]).requires_grad_(True)
+    proj = dev(g["projector"])
+    cv = custma.stereo_matching(cam, proj, 64, k)       # D is accepted and ignored, as in the reference
+    assert cv.shape == g["cost_volume"].shape and cv.dtype == torch.float32
+    assert_cost_close(cv.detach().cpu().numpy(), g["cost_volume"])
+    cv.backward(dev(g["cost_volume_grad"]))
+    assert cam.grad.shape == cam.shape
+    assert_grad_close(cam.grad.cpu().numpy(), g["camera_grad"])
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_direct_kernels_forward_bit_exact_with_reference(name):
+    g = load_golden(name)
+    k = int(g["kernel_size"])
+    cost, best, idx = cb.forward(dev(g["camera"]), dev(g["projector"]), 0, k, want_cost=True, want_wta=True,
+                                 flags=cb.FLAG_DIRECT)
+    assert np.array_equal(cost.cpu().numpy(), g["cost_volume"])
+    tb, ti = torch.from_numpy(g["cost_volume"]).max(dim=-1)
+    assert np.array_equal(best.cpu().numpy(), tb.numpy())
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), ti.numpy())
+    grad = cb.backward(dev(g["cost_volume_grad"]), dev(g["camera"]), dev(g["projector"]), k, 0, flags=cb.FLAG_DIRECT)
+    assert_grad_close(grad.cpu().numpy(), g["camera_grad"])
+
+
+@pytest.mark.parametrize("flags", FLAGS)
+def test_cfg1_reference_fixture(flags):
+    """BASELINE.json configs[0]: 320x240, 5x5 window, forward + WTA + backward."""
+    g = load_golden("cfg1_rand_k5_240x320")
+    k = int(g["kernel_size"])
+    cam, proj = dev(g["camera"]), dev(g["projector"])
+    cost, best, idx = cb.forward(cam, proj, 0, k, want_cost=True, want_wta=True, flags=flags)
+    assert_cost_close(cost[::16, ::16, :].cpu().numpy(), g["cost_sub"])
+    assert_cost_close(best.cpu().numpy(), g["best"])
+    ref_cv = ref_port.forward_full(g["camera"], g["projector"], k)
+    gap = zo.top2_gap(torch.from_numpy(ref_cv)).numpy()
+    sel = gap > COST_TOL
+    assert sel.mean() > 0.99
+    assert np.array_equal(idx.cpu().numpy()[sel], g["argmax"].astype(np.int32)[sel])
+    upstream = dev((g["grad_u"] * g["grad_v"] + g["grad_bias"]).astype(np.float32))
+    grad = cb.backward(upstream, cam, proj, k, 0, flags=flags)
+    assert_grad_close(grad.cpu().numpy(), g["camera_grad"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# banded / batched extension against the CPU oracle (C restatement of the reference kernels)
+# ---------------------------------------------------------------------------------------------------------------
+BANDED_CASES = [  # H, W, D, k
+    (24, 40, 16, 5), (17, 33, 7, 3), (9, 21, 32, 5), (12, 50, 64, 7), (30, 47, 1, 5), (16, 64, 64, 4),
+    (5, 96, 48, 15), (3, 10, 4, 5), (40, 131, 96, 5), (2, 2, 2, 1), (33, 260, 192, 5), (64, 300, 256, 5),
+]
+
+
+@pytest.mark.parametrize("flags", FLAGS)
+@pytest.mark.parametrize("H,W,D,k", BANDED_CASES)
+def test_banded_forward_wta_backward_vs_oracle(H, W, D, k, flags):
+    cam, proj = rand_pair(H, W, seed=H * 1000 + W)
+    ref = ref_port.forward_banded(cam, proj, D, k)
+    cost, best, disp = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True, flags=flags)
+    cost = cost.cpu().numpy()
+    assert cost.shape == (H, W, D)
+    assert_cost_close(cost, ref)
+    invalid = np.arange(W)[:, None] - np.arange(D)[None, :] < 0
+    assert (cost[:, invalid] == cb.INVALID_COST).all()
+    # WTA: identical to the WTA of the kernel's own volume (bit-exact), and to the oracle's outside near-ties
+    ob, od = ref_port.wta_banded(cost)
+    assert np.array_equal(best.cpu().numpy(), ob)
+    assert np.array_equal(disp.cpu().numpy(), od)
+    rb, rd = ref_port.wta_banded(ref)
+    top = np.sort(np.where(invalid[None], -np.inf, ref), axis=-1)
+    gap = top[..., -1] - (top[..., -2] if D > 1 else -np.inf)
+    sel = gap > COST_TOL
+    assert np.array_equal(disp.cpu().numpy()[sel], rd[sel])
+    assert_cost_close(best.cpu().numpy(), rb)
+    # WTA-only call (no volume) gives the same answer
+    b2, d2 = cb.wta(dev(cam), dev(proj), D, k, flags=flags)
+    assert torch.equal(b2, best) and torch.equal(d2, disp)
+    # backward
+    gb = np.random.RandomState(7).randn(H, W, D).astype(np.float32)
+    gref = ref_port.backward_banded(gb, cam, proj, k)
+    grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=flags)
+    assert_grad_close(grad.cpu().numpy(), gref)
+
+
+@pytest.mark.parametrize("flags", FLAGS)
+def test_invalid_cells_carry_no_gradient(flags):
+    H, W, D, k = 12, 20, 16, 5
+    cam, proj = rand_pair(H, W, 3)
+    gb = np.random.RandomState(1).randn(H, W, D).astype(np.float32)
+    gb2 = gb.copy()
+    invalid = np.arange(W)[:, None] - np.arange(D)[None, :] < 0
+    gb2[:, invalid] = 1e6                                         # garbage on invalid cells must not leak
+    a = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=flags)
+    b = cb.backward(dev(gb2), dev(cam), dev(proj), k, D, flags=flags)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("flags", FLAGS)
+def test_batched_equals_per_pair(flags):
+    B, H, W, D, k = 3, 20, 70, 32, 5
+    cam, proj = rand_pair(H, W, 11, B=B)
+    cost, best, disp = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True, flags=flags)
+    gb = np.random.RandomState(2).randn(B, H, W, D).astype(np.float32)
+    grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=flags)
+    assert cost.shape == (B, H, W, D) and grad.shape == (B, H, W)
+    for b in range(B):
+        c1, b1, d1 = cb.forward(dev(cam[b]), dev(proj[b]), D, k, want_cost=True, want_wta=True, flags=flags)
+        assert torch.equal(c1, cost[b]) and torch.equal(b1, best[b]) and torch.equal(d1, disp[b])
+        g1 = cb.backward(dev(gb[b]), dev(cam[b]), dev(proj[b]), k, D, flags=flags)
+        assert torch.equal(g1, grad[b])
+        assert_cost_close(c1.cpu().numpy(), ref_port.forward_banded(cam[b], proj[b], D, k))
+        assert_grad_close(g1.cpu().numpy(), ref_port.backward_banded(gb[b], cam[b], proj[b], k))
+
+
+@pytest.mark.parametrize("kind", ["smooth", "edges", "const"])
+def test_low_contrast_inputs_keep_parity(kind):
+    """Ill-conditioned inputs: the sliding-window path must hand such tiles to the two-pass
+    arithmetic, so costs stay within 1e-5 of the reference-order result."""
+    H, W, D, k = 24, 96, 48, 5
+    rng = np.random.RandomState(5)
+    xx = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)
+    if kind == "smooth":
+        cam = (0.8 + 0.01 * np.sin(xx / 7) + 0.002 * rng.rand(H, W)).astype(np.float32)
+        proj = (0.8 + 0.01 * np.sin((xx + 3) / 7) + 0.002 * rng.rand(H, W)).astype(np.float32)
+    elif kind == "edges":
+        cam = (np.where(xx < W // 2, 0.2, 0.8) + 0.002 * rng.rand(H, W)).astype(np.float32)
+        proj = rng.rand(H, W).astype(np.float32)
+    else:
+        cam = np.full((H, W), 0.5, np.float32)
+        proj = rng.rand(H, W).astype(np.float32)
+    ref = ref_port.forward_banded(cam, proj, D, k)
+    cost, _, _ = cb.forward(dev(cam), dev(proj), D, k)
+    assert_cost_close(cost.cpu().numpy(), ref)
+    gb = rng.randn(H, W, D).astype(np.float32)
+    gref = ref_port.backward_banded(gb, cam, proj, k)
+    grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D)
+    assert_grad_close(grad.cpu().numpy(), gref, tol=2e-5 if kind != "const" else GRAD_TOL)
+
+
+def test_backward_is_deterministic():
+    H, W, D, k = 64, 200, 64, 5
+    cam, proj = rand_pair(H, W, 21)
+    gb = dev(np.random.RandomState(3).randn(H, W, D).astype(np.float32))
+    a = cb.backward(gb, dev(cam), dev(proj), k, D)
+    b = cb.backward(gb, dev(cam), dev(proj), k, D)
+    assert torch.equal(a, b)                                      # the reference's atomics differ run to run
+
+
+def test_autograd_matches_oracle_autograd():
+    H, W, D, k = 20, 48, 24, 5
+    cam, proj = rand_pair(H, W, 31)
+    camt = dev(cam).requires_grad_(True)
+    band = custma.stereo_matching_banded(camt, dev(proj), D, k)
+    w = dev(np.random.RandomState(4).randn(H, W, D).astype(np.float32))
+    valid = torch.from_numpy(np.arange(W)[:, None] - np.arange(D)[None, :] >= 0).cuda()
+    loss = (band * w * valid).sum()
+    loss.backward()
+    auto = zo.camera_grad_banded_autograd(cam, proj, (w * valid).cpu().numpy(), D, k).numpy()
+    assert_grad_close(camt.grad.cpu().numpy(), auto)
+    # the Function returns a gradient for the camera only (custma/stereo_matching_wrapper.py:33)
+    projt = dev(proj).requires_grad_(True)
+    camt2 = dev(cam).requires_grad_(True)
+    custma.stereo_matching(camt2, projt, 0, k).sum().backward()
+    assert projt.grad is None and camt2.grad is not None
+
+
+def test_runs_on_the_current_stream():
+    H, W, D, k = 64, 256, 64, 5
+    cam, proj = rand_pair(H, W, 41)
+    ref, _, _ = cb.forward(dev(cam), dev(proj), D, k)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        c = dev(cam)
+        p = dev(proj)
+        out, _, _ = cb.forward(c, p, D, k)
+    s.synchronize()
+    assert torch.equal(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# error behaviour (custma/include/stereo_matching.hpp:20-29, custma/src/stereo_matching.cpp:23-24,52)
+# ---------------------------------------------------------------------------------------------------------------
+def test_error_behaviour():
+    cam = torch.rand(16, 16, device="cuda")
+    with pytest.raises(RuntimeError, match="camera must be contiguous"):
+        custma.stereo_matching(cam.t(), cam, 4, 5)
+    with pytest.raises(RuntimeError, match="projector must be a CUDA tensor"):
+        custma.stereo_matching(cam, cam.cpu(), 4, 5)
+    with pytest.raises(RuntimeError, match="float32"):
+        custma.stereo_matching(cam.double(), cam.double(), 4, 5)
+    with pytest.raises(RuntimeError, match="same shape"):
+        custma.stereo_matching(cam, cam[:8].contiguous(), 4, 5)
+    with pytest.raises(RuntimeError, match="kernel_size"):
+        custma.stereo_matching(cam, cam, 4, 0)
+    with pytest.raises(RuntimeError, match="kernel_size"):
+        custma.stereo_matching(cam, cam, 4, 33)
+    camg = cam.clone().requires_grad_(True)
+    cv = custma.stereo_matching(camg, cam, 4, 5)
+    with pytest.raises(RuntimeError, match="cost_volume_grad must be contiguous"):
+        cv.backward(torch.ones(16, 16, 1, device="cuda").expand(16, 16, 16))   # reference: CHECK_INPUT at cpp:52
+    with pytest.raises(RuntimeError, match="shape"):
+        custma.src.stereo_matching_backward(torch.ones(16, 16, 8, device="cuda"), cam, cam, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + row-cropped oracle comparison
+# ---------------------------------------------------------------------------------------------------------------
+def _row_crop_check(cam, proj, cost, grad_in, D, k, rows, H):
+    """Oracle on a crop of image rows [h0-r, h1+r): rows h0..h1 of the volume depend on nothing else."""
+    r = k // 2
+    h0, h1 = rows
+    lo, hi = max(0, h0 - r), min(H, h1 + (k - 1 - r))
+    ref = ref_port.forward_banded(cam[lo:hi], proj[lo:hi], D, k)
+    assert_cost_close(cost[h0:h1].cpu().numpy(), ref[h0 - lo:h1 - lo])
+
+
+def test_cfg2_kitti_full_size_forward_wta():
+    """BASELINE.json configs[1]: 1242x375, 192 disparities, forward + WTA."""
+    H, W, D, k = 375, 1242, 192, 5
+    cam, proj = rand_pair(H, W, 2)
+    camd, projd = dev(cam), dev(proj)
+    cost, best, disp = cb.forward(camd, projd, D, k, want_cost=True, want_wta=True)
+    # WTA of the fused kernel == WTA of its own volume, ties to the largest disparity (lowest projector column)
+    flipped = torch.flip(cost, dims=[-1])
+    tb, ti = flipped.max(dim=-1)
+    assert torch.equal(best, tb)
+    assert torch.equal(disp.long(), (D - 1) - ti)
+    b2, d2 = cb.wta(camd, projd, D, k)
+    assert torch.equal(b2, best) and torch.equal(d2, disp)
+    for rows in [(0, 6), (180, 186), (369, 375)]:
+        _row_crop_check(cam, proj, cost, None, D, k, rows, H)
+    # known-answer property: shifting the projector by s0 columns makes disparity s0 the winner with cost ~ 1
+    s0 = 37
+    cam2 = np.zeros_like(proj)
+    cam2[:, s0:] = proj[:, :-s0]
+    b3, d3 = cb.wta(dev(cam2), projd, D, k)
+    inner = (slice(k, H - k), slice(s0 + k, W - k))
+    assert (d3[inner] == s0).all()
+    assert (b3[inner] > 0.9999).all()
+
+
+def test_cfg3_middlebury_full_size_properties():
+    """BASELINE.json configs[2]: 2880x1988, 256 disparities, forward + backward (5.9 GB volume)."""
+    H, W, D, k = 1988, 2880, 256, 5
+    cam, proj = rand_pair(H, W, 3)
+    camd, projd = dev(cam), dev(proj)
+    cost, best, disp = cb.forward(camd, projd, D, k, want_cost=True, want_wta=True)
+    assert cost.shape == (H, W, D)
+    valid = (torch.arange(W, device="cuda")[:, None] - torch.arange(D, device="cuda")[None, :]) >= 0
+    assert bool((cost[:, ~valid] == cb.INVALID_COST).all())
+    assert float(cost[:, valid].abs().max()) <= 1.0 + 1e-5          # ZNCC is a correlation coefficient
+    for rows in [(0, 4), (1000, 1004), (1984, 1988)]:
+        _row_crop_check(cam, proj, cost, None, D, k, rows, H)
+    tb = torch.flip(cost, dims=[-1]).max(dim=-1).values
+    assert torch.equal(best, tb)
+    del tb
+    # backward: linear in the upstream gradient, and equal to the oracle on a cropped band of rows
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    g1 = torch.randn(H, W, D, device="cuda", generator=gen)
+    ga = cb.backward(g1, camd, projd, k, D)
+    g1.mul_(-2.0)
+    gb = cb.backward(g1, camd, projd, k, D)
+    assert_grad_close(gb.cpu().numpy(), (-2.0 * ga).cpu().numpy(), 1e-6)
+    # gradient only of rows [h0,h1): zero the rest, compare with the oracle on the cropped rows
+    h0, h1 = 700, 704
+    g1.zero_()
+    g1[h0:h1] = torch.randn(h1 - h0, W, D, device="cuda", generator=gen)
+    gc = cb.backward(g1, camd, projd, k, D).cpu().numpy()
+    r = k // 2
+    lo, hi = h0 - r, h1 + (k - 1 - r)
+    gsub = np.zeros((hi - lo, W, D), np.float32)
+    gsub[h0 - lo:h1 - lo] = g1[h0:h1].cpu().numpy()
+    gref = ref_port.backward_banded(gsub, cam[lo:hi], proj[lo:hi], k)
+    assert_grad_close(gc[lo:hi], gref)
+    assert np.abs(gc[:lo]).max() == 0 and np.abs(gc[hi:]).max() == 0
