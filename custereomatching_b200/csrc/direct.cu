@@ -123,7 +123,9 @@ int launch_direct_forward(const Problem &p, const float *cam, const float *proj,
 // Backward, step 1: patch gradient of one camera pixel, one warp per pixel, no atomics.
 //   patch_grad[i,j] = sum_d a_d * (proj[h+i-r, d+j-r] - pm_d) - cam_c[i,j] * sum_d b_d
 //   a_d = g_d / den_d,  b_d = g_d * ey2_d * (exy_d + eps) / den_d^3,  den_d = sqrt(ex2 * ey2_d + eps)   (kernel.cu:135-148)
-// Dynamic shared memory per warp: k*k (centred camera patch) + C (the a_d of this pixel).
+// The projector factor is centred BEFORE it is multiplied (as the reference does at :144-145): summing a_d * proj
+// and a_d * pm_d separately cancels catastrophically on low-contrast images.
+// Dynamic shared memory per warp: k*k (centred camera patch) + 2*C (a_d and pm_d of this pixel).
 constexpr int kBwdWarps = 4;
 
 __global__ void __launch_bounds__(kBwdWarps * 32)
@@ -141,33 +143,32 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     const int64_t plane_off = (pix / ((int64_t)p.H * p.W)) * (int64_t)p.H * p.W;
     const float *cam_plane = cam + plane_off, *proj_plane = proj + plane_off;
     const float *pm_row = pmean + plane_off + (int64_t)h * p.W, *ey2_row = pey2 + plane_off + (int64_t)h * p.W;
-    float *camc = smem + (size_t)warp * (kk + p.C);
+    float *camc = smem + (size_t)warp * (kk + 2 * p.C);
     float *a_s = camc + kk;
+    float *pm_s = a_s + p.C;
     const float cm = cmean[pix], ex2 = cex2[pix];
     for (int t = lane; t < kk; t += 32)
         camc[t] = query_ij(cam_plane, p.H, p.W, h + t / p.k - p.r, w + t % p.k - p.r) - cm;
     __syncwarp();
 
-    float bsum = 0.f, am = 0.f;
+    float bsum = 0.f;
     for (int c = lane; c < p.C; c += 32) {
         const int d = p.banded ? w - c : c;
-        float a = 0.f;
+        float a = 0.f, pm = 0.f;
         if (d >= 0) {
-            const float pm = pm_row[d], ey2 = ey2_row[d];
+            pm = pm_row[d];
+            const float ey2 = ey2_row[d];
             const float exy = cell_exy(camc, proj_plane, p.H, p.W, p.k, p.r, h, d, pm);
             const float den = sqrtf(fmaf(ex2, ey2, kEps));
             const float g = grad[pix * p.C + c];
             a = g / den;
             bsum += g * ey2 * (exy + kEps) / (den * den * den);
-            am = fmaf(a, pm, am);
         }
         a_s[c] = a;
+        pm_s[c] = pm;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-        am += __shfl_xor_sync(0xffffffffu, am, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     __syncwarp();
     for (int t = 0; t < kk; ++t) {
         const int y = h + t / p.k - p.r, xo = t % p.k - p.r;
@@ -177,12 +178,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
             for (int c = lane; c < p.C; c += 32) {
                 const int d = p.banded ? w - c : c;
                 const int x = d + xo;
-                if (d >= 0 && x >= 0 && x < p.W) acc = fmaf(a_s[c], __ldg(prow + x), acc);
+                if (d >= 0) acc = fmaf(a_s[c], ((x >= 0 && x < p.W) ? __ldg(prow + x) : 0.f) - pm_s[c], acc);
             }
+        } else {
+            for (int c = lane; c < p.C; c += 32) acc = fmaf(a_s[c], -pm_s[c], acc);  // zero-padded row: proj = 0
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) patch_grad[pix * kk + t] = acc - am - bsum * camc[t];
+        if (lane == 0) patch_grad[pix * kk + t] = acc - bsum * camc[t];
     }
 }
 
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(256)
 int launch_direct_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
                            const float *cmean, const float *cex2, const float *pmean, const float *pey2,
                            float *patch_grad, float *camera_grad, cudaStream_t stream) {
-    const size_t smem = (size_t)kBwdWarps * (p.k * p.k + p.C) * sizeof(float);
+    const size_t smem = (size_t)kBwdWarps * (p.k * p.k + 2 * p.C) * sizeof(float);
     if (smem > 200 * 1024)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "direct backward: last axis %d too long for shared memory", p.C);
     if (smem > 48 * 1024)

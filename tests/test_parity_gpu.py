@@ -198,7 +198,10 @@ def test_autograd_matches_oracle_autograd():
     # the Function returns a gradient for the camera only (custma/stereo_matching_wrapper.py:33)
     projt = dev(proj).requires_grad_(True)
     camt2 = dev(cam).requires_grad_(True)
-    custma.stereo_matching(camt2, projt, 0, k).sum().backward()
+    cv = custma.stereo_matching(camt2, projt, 0, k)
+    # .sum().backward() would hand over an expanded (non-contiguous) gradient, which the reference rejects
+    # (CHECK_INPUT at custma/src/stereo_matching.cpp:52) and so does this implementation (test_error_behaviour)
+    cv.backward(torch.ones_like(cv))
     assert projt.grad is None and camt2.grad is not None
 
 
