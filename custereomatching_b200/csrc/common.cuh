@@ -60,7 +60,8 @@ int launch_direct_backward(const Problem &p, const float *grad, const float *cam
 
 // sliding-window kernels (sliding_forward.cu / sliding_backward.cu); return CUSTMA_ERR_UNSUPPORTED if the
 // (k, mode) combination has no instantiation, in which case the caller falls back to the direct kernels.
-bool sliding_supported(const Problem &p);
+bool sliding_forward_supported(const Problem &p);
+bool sliding_backward_supported(const Problem &p);
 size_t sliding_forward_workspace_bytes(const Problem &p);
 size_t sliding_backward_workspace_bytes(const Problem &p);
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,

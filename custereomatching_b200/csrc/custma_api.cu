@@ -64,13 +64,18 @@ static int carve_stats(const Problem &p, void *ws, size_t ws_bytes, size_t need,
     return CUSTMA_OK;
 }
 
-static bool use_sliding(const Problem &p, uint32_t flags) { return !(flags & CUSTMA_FLAG_DIRECT) && sliding_supported(p); }
+static bool use_sliding_fwd(const Problem &p, uint32_t flags) {
+    return !(flags & CUSTMA_FLAG_DIRECT) && sliding_forward_supported(p);
+}
+static bool use_sliding_bwd(const Problem &p, uint32_t flags) {
+    return !(flags & CUSTMA_FLAG_DIRECT) && sliding_backward_supported(p);
+}
 
 static size_t forward_ws(const Problem &p, uint32_t flags) {
-    return stats_bytes(p) + (use_sliding(p, flags) ? sliding_forward_workspace_bytes(p) : 0);
+    return stats_bytes(p) + (use_sliding_fwd(p, flags) ? sliding_forward_workspace_bytes(p) : 0);
 }
 static size_t backward_ws(const Problem &p, uint32_t flags) {
-    if (use_sliding(p, flags)) return stats_bytes(p) + sliding_backward_workspace_bytes(p);
+    if (use_sliding_bwd(p, flags)) return stats_bytes(p) + sliding_backward_workspace_bytes(p);
     return stats_bytes(p) + align256((size_t)p.pixels() * p.k * p.k * sizeof(float));
 }
 
@@ -109,8 +114,8 @@ int custma_forward(const float *camera, const float *projector, float *cost_volu
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
     if ((rc = carve_stats(p, workspace, workspace_bytes, forward_ws(p, flags), &s))) return rc;
-    if (use_sliding(p, flags))
-        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, workspace, workspace_bytes, stream);
+    if (use_sliding_fwd(p, flags))
+        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, s.rest, s.rest_bytes, stream);
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream);
@@ -128,8 +133,8 @@ int custma_backward(const float *cost_volume_grad, const float *camera, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
     if ((rc = carve_stats(p, workspace, workspace_bytes, backward_ws(p, flags), &s))) return rc;
-    if (use_sliding(p, flags))
-        return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, workspace, workspace_bytes, stream);
+    if (use_sliding_bwd(p, flags))
+        return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, s.rest, s.rest_bytes, stream);
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,

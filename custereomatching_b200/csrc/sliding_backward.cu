@@ -1,0 +1,486 @@
+// Sliding-window backward: gradient of the ZNCC volume with respect to the camera image, one pass over the upstream
+// gradient (4 bytes per cell read once), no global atomics, deterministic.
+//
+// What it restates: get_patches_grad_kernel + patches_grad_to_image_kernel (reference
+// custma/src/stereo_matching_kernel.cu:75-152, :155-179).  The reference recomputes the window moments of every cell
+// (6k^2 loads) and then issues k^2 same-address global atomics per cell.  Here (checked against
+// autograd by the oracle tests), with a = g/den and bc = g*ey2*(exy+eps)/den^3 per cell (reference :135,:145-148):
+//
+//   camera_grad[y,x] = T1[y,x] - sum_{(h,w) covering (y,x)} ( Am[h,w] + Bs[h,w] * (cam[y,x] - cmean[h,w]) )
+//   T1[y,x] = sum_s proj'[y,x-s] * (k x k box sum over (h,w) of a[h,w,s])     <- this kernel, per tile
+//   Am[h,w] = sum_s a[h,w,s] * pmean'[h,w-s],   Bs[h,w] = sum_s bc[h,w,s]        <- this kernel, per pixel
+//
+// The main kernel marches down a row band like the forward does (same thread tile: 4 columns x 4 disparities, same
+// pair-sum ring to recompute exy), keeps a second ring for the vertical k-row sum of a, convolves it horizontally in
+// registers, multiplies by the projector row of the TARGET image row and reduces over the 16 lanes of a unit with a
+// shuffle reduce-scatter.  Per-unit partial sums go to shared memory and are added in a fixed order two steps later;
+// per-tile T1 rows and per-pixel Am / Bs go to the workspace, and sliding_backward_finalize_kernel gathers them.
+// The upstream gradient is prefetched with per-thread cp.async (each thread reads back only what it copied, so no
+// barrier is involved), three row steps ahead.
+#include "sliding_common.cuh"
+
+namespace custma {
+
+constexpr int kGradStages = 4;     // ring of upstream-gradient rows in shared memory
+constexpr int kGradLookahead = 3;  // steps between issuing a gradient row and using it
+
+template <int K, int NU, int WG>
+struct BwdGeom {
+    using F = SlideGeom<K, NU, WG>;
+    static constexpr int OFF_PROJ = F::SEG_CAM, OFF_PROJT = OFF_PROJ + F::SEG_PROJ, OFF_A = OFF_PROJT + F::SEG_PROJ,
+                         OFF_EX2 = OFF_A + F::SEG_CS, OFF_SP = OFF_EX2 + F::SEG_CS, OFF_EY2 = OFF_SP + F::SEG_PS,
+                         OFF_STG = OFF_EY2 + F::SEG_PS;
+    static constexpr int UNITS = NU * WG;
+    static constexpr int SLOT = OFF_STG + 16 * UNITS;            // + one reduced value per lane of every unit
+    static constexpr int CHUNKS = OFF_STG / 4, NCH = (CHUNKS + F::NCONS - 1) / F::NCONS;
+    static constexpr int TW = F::WTC + K - 1;                    // columns of a T1 tile row
+    static_assert(TW <= 64 && 64 + 2 * F::WTC <= F::NCONS, "reduce_step thread ranges");
+    static constexpr size_t SMEM_BYTES = ((size_t)F::NS * SLOT + (size_t)kGradStages * 16 * F::NCONS) * sizeof(float);
+};
+
+// extra workspace of the backward, after the forward-style arrays (SlidingLayout::off_extra)
+struct BwdLayout {
+    int32_t TW, TH;              // T1 tile: TH = RBH rows x TW columns
+    size_t off_T1, off_Am, off_Bs, total;
+};
+
+static void make_bwd_layout(const Problem &p, const SlidingLayout &L, BwdLayout *BL) {
+    BL->TW = L.WTC + L.K - 1;
+    BL->TH = L.RBH;
+    size_t off = L.off_extra;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t tiles = (size_t)p.B * L.NB * L.n_wtiles * L.n_chunks;
+    BL->off_T1 = take(tiles * BL->TH * BL->TW * sizeof(float));
+    const size_t rows = (size_t)p.B * L.n_chunks * L.NB * L.RB;
+    BL->off_Am = take(rows * L.cs_pitch * sizeof(float));
+    BL->off_Bs = take(rows * L.cs_pitch * sizeof(float));
+    BL->total = off;
+}
+
+// loader of the backward row steps: like RowLoader, plus the projector row of the target image row (k-1 steps old)
+template <int K, int NU, int WG>
+struct BwdRowLoader {
+    using F = SlideGeom<K, NU, WG>;
+    using G = BwdGeom<K, NU, WG>;
+    const float *src[G::NCH];
+    int stride[G::NCH], dst[G::NCH], first[G::NCH], last[G::NCH];
+    __device__ __forceinline__ void init(const SlidingLayout &L, const char *ws, int b, int nb, int h0, int w_base,
+                                         int s_base) {
+        const int xlo = w_base - F::r - s_base - F::SC + 1, dlo = w_base - s_base - F::SC + 1;
+        const int64_t band = (int64_t)b * L.NB + nb;
+        const int64_t srow = ((int64_t)b * L.NB * L.RB + h0) - (K - 1);
+#pragma unroll
+        for (int n = 0; n < G::NCH; ++n) {
+            const int off = 4 * ((int)threadIdx.x + n * F::NCONS);
+            dst[n] = off < G::OFF_STG ? off : -1;
+            if (off < G::OFF_PROJ) {
+                first[n] = 0; last[n] = L.RBH; stride[n] = L.cam_pitch;
+                src[n] = (const float *)(ws + L.off_camP) + band * L.RBH * L.cam_pitch + (w_base - F::r + L.cam_lc) + off;
+            } else if (off < G::OFF_PROJT) {
+                first[n] = 0; last[n] = L.RBH; stride[n] = L.proj_pitch;
+                src[n] = (const float *)(ws + L.off_projP) + band * L.RBH * L.proj_pitch + (xlo + L.proj_lp) + (off - G::OFF_PROJ);
+            } else if (off < G::OFF_A) {
+                first[n] = K - 1; last[n] = L.RBH + K - 1; stride[n] = L.proj_pitch;
+                src[n] = (const float *)(ws + L.off_projP) + (band * L.RBH - (K - 1)) * L.proj_pitch + (xlo + L.proj_lp) + (off - G::OFF_PROJT);
+            } else if (off < G::OFF_EX2) {
+                first[n] = K - 1; last[n] = L.RB + K - 1; stride[n] = L.cs_pitch;
+                src[n] = (const float *)(ws + L.off_A) + srow * L.cs_pitch + w_base + (off - G::OFF_A);
+            } else if (off < G::OFF_SP) {
+                first[n] = K - 1; last[n] = L.RB + K - 1; stride[n] = L.cs_pitch;
+                src[n] = (const float *)(ws + L.off_ex2) + srow * L.cs_pitch + w_base + (off - G::OFF_EX2);
+            } else if (off < G::OFF_EY2) {
+                first[n] = K - 1; last[n] = L.RB + K - 1; stride[n] = L.ps_pitch;
+                src[n] = (const float *)(ws + L.off_Sp) + srow * L.ps_pitch + (dlo + L.ps_ld) + (off - G::OFF_SP);
+            } else {
+                first[n] = K - 1; last[n] = L.RB + K - 1; stride[n] = L.ps_pitch;
+                src[n] = (const float *)(ws + L.off_ey2) + srow * L.ps_pitch + (dlo + L.ps_ld) + (off - G::OFF_EY2);
+            }
+        }
+    }
+    // in order t = 0, 1, 2, ...; the caller has already waited for the slot to be empty
+    __device__ __forceinline__ void issue(int t, float *smem, uint64_t *full_bar) {
+        const int slot = t & (F::NS - 1);
+        float *S = smem + slot * G::SLOT;
+#pragma unroll
+        for (int n = 0; n < G::NCH; ++n) {
+            if (dst[n] >= 0 && t >= first[n] && t < last[n]) cp_async16(S + dst[n], src[n]);
+            src[n] += stride[n];
+        }
+        cp_async_mbar_arrive(&full_bar[slot]);
+    }
+};
+
+// vertical k-row sum of a value stream through the pair-sum ring (same recurrence as BoxRing, no products)
+template <int K>
+struct SumRing {
+    float prev[4][4];
+    float P[K - 2][4][4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                prev[i][j] = 0.f;
+#pragma unroll
+                for (int m = 0; m < K - 2; ++m) P[m][i][j] = 0.f;
+            }
+    }
+    __device__ __forceinline__ void step(const int Q, const float (&a)[4][4], float (&sum)[4][4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = a[i][j];
+#pragma unroll
+                for (int m = 1; m <= K - 2; m += 2) s += P[(Q - m + 2 * (K - 2)) % (K - 2)][i][j];
+                P[Q][i][j] = a[i][j] + prev[i][j];
+                prev[i][j] = a[i][j];
+                sum[i][j] = s;
+            }
+    }
+};
+
+template <int K, int NU, int WG, bool EDGE>
+__device__ __forceinline__ void backward_consumer(const Problem &p, const SlidingLayout &L, float *smem,
+                                                  uint64_t *full_bar, uint64_t *empty_bar,
+                                                  BwdRowLoader<K, NU, WG> &loader, int b, int h0, int rows, int w_base,
+                                                  int s_base, int steps, const float *__restrict__ grad,
+                                                  float *__restrict__ T1tile, float *__restrict__ AmRow,
+                                                  float *__restrict__ BsRow) {
+    using F = SlideGeom<K, NU, WG>;
+    using G = BwdGeom<K, NU, WG>;
+    constexpr int CL = F::CL, PL = F::PL, NS = F::NS, PERIOD = F::PERIOD, NT = F::NCONS;
+    const int tid = threadIdx.x;
+    const int l16 = tid & 15, u = tid >> 4, su = u % NU, wg = u / NU;
+    const int w0 = w_base + 4 * wg, s0 = s_base + 64 * su + 4 * l16;
+    const int pidx = 4 * (wg - 16 * su - l16 + 16 * NU - 1);
+    const int C = p.C;
+    const float seed = kEps / (float)K, inv_n = 1.f / (float)(K * K);
+    float *gsm = smem + NS * G::SLOT;   // [kGradStages][4][NT] float4
+    // upstream gradient of (row h0, column w0, disparity s0); row hr, column i: + (hr*W + i) * C
+    const float *gsrc = grad + (((int64_t)b * p.H + h0) * p.W + w0) * C + (EDGE ? 0 : s0);
+    const int64_t g_row = (int64_t)p.W * C;
+
+    BoxRing<K> ring;
+    SumRing<K> vring;
+    ring.clear();
+    vring.clear();
+
+    // fixed-order sum of the per-unit partials of step ts (every warp has arrived on its empty barrier) -> workspace
+    auto reduce_step = [&](int ts) {
+        if (ts < K - 1) return;
+        const int ty = ts - (K - 1);
+        const float *stg = smem + (ts & (NS - 1)) * G::SLOT + G::OFF_STG;
+        if (tid < G::TW) {
+            if (ty < L.RBH) {
+                const int x = tid;
+                float acc = 0.f;
+#pragma unroll
+                for (int g = 0; g < WG; ++g) {
+                    const int xi = x - 4 * g;
+                    if (xi >= 0 && xi < K + 3) {
+#pragma unroll
+                        for (int q = 0; q < NU; ++q) acc += stg[(g * NU + q) * 16 + xi];
+                    }
+                }
+                T1tile[(int64_t)ty * G::TW + x] = acc;
+            }
+        } else if (tid >= 64 && tid < 64 + 2 * F::WTC) {
+            if (ty < rows) {
+                const int idx = tid - 64, w = idx % F::WTC, which = idx / F::WTC;  // 0: Bs, 1: Am
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < NU; ++q) acc += stg[((w >> 2) * NU + q) * 16 + 8 + 4 * which + (w & 3)];
+                (which ? AmRow : BsRow)[(int64_t)ty * L.cs_pitch + w] = which ? acc * inv_n : acc;
+            }
+        }
+    };
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += PERIOD) {
+#pragma unroll
+        for (int q = 0; q < PERIOD; ++q) {
+            const int t = t0 + q;
+            const int slot = t & (NS - 1);
+            // ---- refill the slot of step t + lookahead (used last by step t - 2), after finishing that step's sums
+            if (t >= 2) {
+                mbar_wait(&empty_bar[(t - 2) & (NS - 1)], ((t - 2) / NS) & 1);
+                reduce_step(t - 2);
+            }
+            if (t + kLookahead < steps) loader.issue(t + kLookahead, smem, full_bar);
+            // ---- prefetch the upstream gradient row that step t + kGradLookahead consumes
+            if (!EDGE) {
+                const int hp = t + kGradLookahead - (K - 1);
+                if (hp >= 0 && hp < rows) {
+                    float *gdst = gsm + ((hp & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * C);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            mbar_wait(&full_bar[slot], (t / NS) & 1);
+            float *S = smem + slot * G::SLOT;
+
+            float a[4][4];
+            float red[16];  // T1[0..8), Bs[0..4), Am[0..4)
+#pragma unroll
+            for (int n = 0; n < 16; ++n) red[n] = 0.f;
+            const int hr = t - (K - 1);
+            if (t < L.RBH) {
+                float c[CL], pj[PL];
+#pragma unroll
+                for (int v = 0; v < CL / 4; ++v)
+                    *reinterpret_cast<float4 *>(&c[4 * v]) = *reinterpret_cast<const float4 *>(S + 4 * wg + 4 * v);
+#pragma unroll
+                for (int v = 0; v < PL / 4; ++v)
+                    *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
+                float bx[4][4];
+                ring.step(q, c, pj, seed, bx);
+                if (hr >= 0 && hr < rows) {
+                    float a4[4], e4[4], sp[8], ey[8], gg[4][4];
+                    *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
+                    *reinterpret_cast<float4 *>(e4) = *reinterpret_cast<const float4 *>(S + G::OFF_EX2 + 4 * wg);
+                    *reinterpret_cast<float4 *>(&sp[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx);
+                    *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
+                    *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
+                    *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
+                    if (!EDGE) {
+                        asm volatile("cp.async.wait_group %0;" ::"n"(kGradLookahead) : "memory");
+                        const float *gs = gsm + ((hr & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int s = s0 + j, d = w0 + i - s;
+                                const bool valid = w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s < p.D);
+                                gg[i][j] = valid ? __ldg(gsrc + hr * g_row + (int64_t)i * C + (p.banded ? s : d)) : 0.f;
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float bs = 0.f, am = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int di = i - j + 3;
+                            const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
+                            const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
+                            const float av = gg[i][j] * rs;                              // a  = g / den        (:135,:145)
+                            const float bc = (av * e) * (ey[di] * (rs * rs));            // bc = g*ey2*(exy+eps)/den^3 (:147)
+                            a[i][j] = av;
+                            bs += bc;
+                            am = fmaf(av, sp[di], am);
+                        }
+                        red[8 + i] = bs;
+                        red[12 + i] = am;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+            }
+            // ---- vertical k-row sum of a, then the target row y = hr - r:  T1[x] += proj'[y, x - s] * sum_w va[w][s]
+            float va[4][4];
+            vring.step(q, a, va);
+            if (t >= K - 1) {
+                float pt[PL];
+#pragma unroll
+                for (int v = 0; v < PL / 4; ++v)
+                    *reinterpret_cast<float4 *>(&pt[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJT + pidx + 4 * v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // target column xi (relative to w0 - r) is covered by cells w_i with xi - (K-1) <= i <= xi
+#pragma unroll
+                    for (int xi = 0; xi < K + 3; ++xi) {
+                        float h = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i <= xi && i >= xi - (K - 1)) h += va[i][j];
+                        red[xi] = fmaf(pt[xi - j + 3], h, red[xi]);
+                    }
+                }
+            }
+            // ---- reduce the 16 partial sums over the 16 lanes of the unit (reduce-scatter): lane l ends with value #l
+            {
+                const bool b8 = l16 & 8, b4 = l16 & 4, b2 = l16 & 2, b1 = l16 & 1;
+                float k8[8], k4[4], k2[2];
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                    k8[n] = (b8 ? red[n + 8] : red[n]) + __shfl_xor_sync(0xffffffffu, b8 ? red[n] : red[n + 8], 8);
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+                    k4[n] = (b4 ? k8[n + 4] : k8[n]) + __shfl_xor_sync(0xffffffffu, b4 ? k8[n] : k8[n + 4], 4);
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+                    k2[n] = (b2 ? k4[n + 2] : k4[n]) + __shfl_xor_sync(0xffffffffu, b2 ? k4[n] : k4[n + 2], 2);
+                const float k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k2[0] : k2[1], 1);
+                S[G::OFF_STG + u * 16 + l16] = k1;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
+        }
+    }
+    // the sums of the last two steps
+    for (int ts = steps - 2; ts < steps; ++ts) {
+        if (ts < 0) continue;
+        mbar_wait(&empty_bar[ts & (NS - 1)], (ts / NS) & 1);
+        reduce_step(ts);
+    }
+}
+
+template <int K, int NU, int WG>
+__global__ void __launch_bounds__(16 * NU * WG, 2)
+    sliding_backward_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
+                            const float *__restrict__ grad) {
+    using F = SlideGeom<K, NU, WG>;
+    constexpr int WTC = F::WTC, SC = F::SC, NS = F::NS, NCW = F::NCW;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+
+    const int tid = threadIdx.x;
+    const int wt = blockIdx.x / L.n_chunks, ch = blockIdx.x % L.n_chunks, nb = blockIdx.y, b = blockIdx.z;
+    const int w_base = wt * WTC, s_base = chunk_s_base(L, p.W, w_base, ch), h0 = nb * L.RB;
+    const int rows = min(L.RB, p.H - h0);
+    // row steps: RBH to run every image row through the window ring + k-1 to flush the vertical ring of a
+    const int steps = (L.RBH + K - 1 + F::PERIOD - 1) / F::PERIOD * F::PERIOD;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full_bar[i], F::NCONS);
+            mbar_init(&empty_bar[i], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    BwdRowLoader<K, NU, WG> loader;
+    loader.init(L, ws, b, nb, h0, w_base, s_base);
+    for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar);
+
+    const int64_t tile = (((int64_t)b * L.NB + nb) * L.n_wtiles + wt) * L.n_chunks + ch;
+    float *T1tile = (float *)(ws + BL.off_T1) + tile * BL.TH * BL.TW;
+    const int64_t prow = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h0) * L.cs_pitch + w_base;
+    float *AmRow = (float *)(ws + BL.off_Am) + prow, *BsRow = (float *)(ws + BL.off_Bs) + prow;
+
+    const bool interior = p.banded && (p.D & 3) == 0 && rows == L.RB && w_base + WTC <= p.W && s_base + SC <= p.D &&
+                          w_base - (s_base + SC - 1) >= 0;
+    if (interior)
+        backward_consumer<K, NU, WG, false>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
+                                            grad, T1tile, AmRow, BsRow);
+    else
+        backward_consumer<K, NU, WG, true>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
+                                           grad, T1tile, AmRow, BsRow);
+}
+
+// camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of
+// ( Am[h,w] + Bs[h,w] * (cam'[y,x] - A[h,w]) ), cam' and A relative to the pivot of the band of row h.
+// Fixed summation order; out-of-image cells do not exist, out-of-image targets are never computed (reference :177).
+__global__ void __launch_bounds__(256)
+    sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
+                                     const char *__restrict__ ws, float *__restrict__ camera_grad) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.pixels()) return;
+    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), b = (int)(pix / ((int64_t)p.H * p.W));
+    const int K = L.K, r = L.r;
+    const float *T1 = (const float *)(ws + BL.off_T1);
+    const float *Am = (const float *)(ws + BL.off_Am), *Bs = (const float *)(ws + BL.off_Bs);
+    const float *A = (const float *)(ws + L.off_A), *camP = (const float *)(ws + L.off_camP);
+    float acc = 0.f;
+    // T1 tiles: band nb covers target rows [nb*RB - r, nb*RB + RBH - r), tile wt covers columns [wt*WTC - r, wt*WTC + TW - r)
+    for (int nb = max(0, (y + r - L.RBH + 1) / L.RB); nb < L.NB && nb * L.RB - r <= y; ++nb) {
+        const int ty = y - (nb * L.RB - r);
+        if (ty < 0 || ty >= L.RBH) continue;
+        for (int wt = max(0, (x + r - BL.TW + 1) / L.WTC); wt < L.n_wtiles && wt * L.WTC - r <= x; ++wt) {
+            const int tx = x - (wt * L.WTC - r);
+            if (tx < 0 || tx >= BL.TW) continue;
+            for (int ch = 0; ch < L.n_chunks; ++ch) {
+                const int64_t tile = (((int64_t)b * L.NB + nb) * L.n_wtiles + wt) * L.n_chunks + ch;
+                acc += T1[(tile * BL.TH + ty) * BL.TW + tx];
+            }
+        }
+    }
+    float sub = 0.f;
+    for (int i = 0; i < K; ++i) {
+        const int h = y - i + r;
+        if (h < 0 || h >= p.H) continue;
+        const int nb = h / L.RB;
+        const float cv = camP[(((int64_t)b * L.NB + nb) * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
+        for (int j = 0; j < K; ++j) {
+            const int w = x - j + r;
+            if (w < 0 || w >= p.W) continue;
+            const float av = A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w];
+            float am = 0.f, bs = 0.f;
+            for (int ch = 0; ch < L.n_chunks; ++ch) {
+                const int64_t o = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h) * L.cs_pitch + w;
+                am += Am[o];
+                bs += Bs[o];
+            }
+            sub += fmaf(bs, cv - av, am);
+        }
+    }
+    camera_grad[pix] = acc - sub;
+}
+
+template <int K, int NU, int WG>
+static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws, const float *grad,
+                          cudaStream_t stream) {
+    const size_t smem = BwdGeom<K, NU, WG>::SMEM_BYTES;
+    auto kern = sliding_backward_kernel<K, NU, WG>;
+    CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
+    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad);
+    CUSTMA_LAUNCH_CHECK("sliding_backward_kernel");
+    return CUSTMA_OK;
+}
+
+bool sliding_backward_supported(const Problem &p) {
+    SlidingConfig cfg;
+    return sliding_pick_config(p, &cfg);
+}
+
+size_t sliding_backward_workspace_bytes(const Problem &p) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, &cfg)) return 0;
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, true, &L);
+    BwdLayout BL;
+    make_bwd_layout(p, L, &BL);
+    return BL.total;
+}
+
+int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
+                            float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, true, &L);
+    BwdLayout BL;
+    make_bwd_layout(p, L, &BL);
+    if (workspace_bytes < BL.total)
+        return set_error(CUSTMA_ERR_WORKSPACE, "sliding backward needs %zu workspace bytes, %zu given", BL.total, workspace_bytes);
+    char *ws = (char *)workspace;
+    int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
+    if (rc) return rc;
+    switch (cfg.NU) {
+        case 1: rc = launch_bwd_cfg<5, 1, 12>(p, L, BL, ws, grad, stream); break;
+        case 2: rc = launch_bwd_cfg<5, 2, 6>(p, L, BL, ws, grad, stream); break;
+        case 3: rc = launch_bwd_cfg<5, 3, 4>(p, L, BL, ws, grad, stream); break;
+        default: rc = launch_bwd_cfg<5, 4, 3>(p, L, BL, ws, grad, stream); break;
+    }
+    if (rc) return rc;
+    sliding_backward_finalize_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, L, BL, ws, camera_grad);
+    CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
+    return CUSTMA_OK;
+}
+
+}  // namespace custma

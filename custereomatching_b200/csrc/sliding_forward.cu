@@ -1,13 +1,264 @@
-// placeholder until the sliding-window kernels land
-#include "common.cuh"
+// Sliding-window forward: ZNCC cost volume + winner-take-all in O(1) work per cell (for the tiling see
+// sliding_common.cuh).
+//
+// What it restates: forward_cost_volume_kernel (reference custma/src/stereo_matching_kernel.cu:17-72) and the WTA the
+// examples run in torch (examples/verify.py:72-74).  The reference evaluates the k x k window of every cell from
+// scratch (4k^2 loads per cell); here, for a fixed disparity s, the raw correlation sum(cam' * proj') over the window
+// is a k x k box filter of the product image q_s[y,x] = cam'[y,x] * proj'[y,x-s]:
+//   horizontal   k-term FMA chain for the first of a thread's 4 columns, then 2 FMAs per further column
+//                (add the entering product, subtract the leaving one)
+//   vertical     register ring of the last k-1 horizontal sums while the thread marches down the rows
+//   epilogue     exy = box - A[h,w] * Sp[h,d]   (A = window mean of cam', Sp = window sum of proj', both pivoted)
+//                cost = (exy + eps) * rsqrt(ex2[h,w] * ey2[h,d] + eps)                      (reference :71)
+// The pivoted image rows and the per-pixel statistics of each row step arrive in an 8-slot shared-memory ring through
+// cp.async + mbarrier (RowLoader, sliding_common.cuh), six steps ahead of their use; there is no __syncthreads in the
+// row loop, and the only other global traffic is the volume itself (one 128-bit streaming store per 4 cells) and the
+// WTA keys.
+#include "sliding_common.cuh"
+
 namespace custma {
-bool sliding_supported(const Problem &) { return false; }
-size_t sliding_forward_workspace_bytes(const Problem &) { return 0; }
-size_t sliding_backward_workspace_bytes(const Problem &) { return 0; }
-int launch_sliding_forward(const Problem &, const float *, const float *, float *, float *, int32_t *, void *, size_t, cudaStream_t) {
-    return set_error(CUSTMA_ERR_UNSUPPORTED, "sliding forward not built");
+
+
+
+template <int K, int NU, int WG, bool EDGE, bool COST, bool WTA>
+__device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
+                                                 uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
+                                                 int h0, int rows, int w_base, int s_base, int steps,
+                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys);
+
+
+template <int K, int NU, int WG, bool COST, bool WTA>
+__global__ void __launch_bounds__(16 * NU * WG, 2)
+    sliding_forward_kernel(const Problem p, const SlidingLayout L, const char *__restrict__ ws,
+                           float *__restrict__ cost, unsigned long long *__restrict__ wta_keys) {
+    using G = SlideGeom<K, NU, WG>;
+    constexpr int WTC = G::WTC, SC = G::SC, NS = G::NS, NCW = G::NCW;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+
+    const int tid = threadIdx.x;
+    const int wt = blockIdx.x / L.n_chunks, ch = blockIdx.x % L.n_chunks, nb = blockIdx.y, b = blockIdx.z;
+    const int w_base = wt * WTC, s_base = chunk_s_base(L, p.W, w_base, ch), h0 = nb * L.RB;
+    const int rows = min(L.RB, p.H - h0);
+    // row steps, padded to whole periods of the pair-sum ring (the band copies and statistics rows cover the padding)
+    const int steps = (rows + K - 1 + G::PERIOD - 1) / G::PERIOD * G::PERIOD;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full_bar[i], G::NCONS);
+            mbar_init(&empty_bar[i], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    RowLoader<K, NU, WG> loader;
+    loader.init(L, ws, b, nb, h0, w_base, s_base);
+    for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar, empty_bar);
+
+    // tiles whose every cell is a valid, 16-byte aligned store take the check-free body
+    const bool interior = p.banded && (p.D & 3) == 0 && rows == L.RB && w_base + WTC <= p.W && s_base + SC <= p.D &&
+                          w_base - (s_base + SC - 1) >= 0;
+    if (interior)
+        forward_consumer<K, NU, WG, false, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base,
+                                                      s_base, steps, cost, wta_keys);
+    else
+        forward_consumer<K, NU, WG, true, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base,
+                                                     s_base, steps, cost, wta_keys);
 }
-int launch_sliding_backward(const Problem &, const float *, const float *, const float *, float *, void *, size_t, cudaStream_t) {
-    return set_error(CUSTMA_ERR_UNSUPPORTED, "sliding backward not built");
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
+    return __shfl_xor_sync(0xffffffffu, v, o);
 }
+__device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+template <int K, int NU, int WG, bool EDGE, bool COST, bool WTA>
+__device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
+                                                 uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
+                                                 int h0, int rows, int w_base, int s_base, int steps,
+                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys) {
+    using G = SlideGeom<K, NU, WG>;
+    constexpr int CL = G::CL, PL = G::PL, NS = G::NS, PERIOD = G::PERIOD;
+    const int tid = threadIdx.x;
+    const int l16 = tid & 15, u = tid >> 4, su = u % NU, wg = u / NU;
+    const int w0 = w_base + 4 * wg, s0 = s_base + 64 * su + 4 * l16;
+    const int pidx = 4 * (wg - 16 * su - l16 + 16 * NU - 1);
+    const int C = p.C;
+    // pixel (h0 - (K-1), w0): output row of step t is h0 + t - (K-1), so the running pointers start k-1 rows early
+    const int64_t pix_start = ((int64_t)b * p.H + h0 - (K - 1)) * p.W + w0;
+    float *out = COST ? cost + pix_start * C + (EDGE ? 0 : s0) : nullptr;
+    unsigned long long *keys = WTA ? wta_keys + pix_start : nullptr;
+    const int64_t out_row = (int64_t)p.W * C;
+    const float seed = kEps / (float)K;
+
+    BoxRing<K> ring;
+    ring.clear();
+
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += PERIOD) {
+#pragma unroll
+        for (int q = 0; q < PERIOD; ++q) {
+            const int t = t0 + q;
+            const int slot = t & (NS - 1);
+            if (t + kLookahead < steps) loader.issue(t + kLookahead, smem, full_bar, empty_bar);
+            mbar_wait(&full_bar[slot], (t / NS) & 1);
+            const float *S = smem + slot * G::SLOT;
+            float c[CL], pj[PL];
+#pragma unroll
+            for (int v = 0; v < CL / 4; ++v)
+                *reinterpret_cast<float4 *>(&c[4 * v]) = *reinterpret_cast<const float4 *>(S + 4 * wg + 4 * v);
+#pragma unroll
+            for (int v = 0; v < PL / 4; ++v)
+                *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
+            float bx[4][4];
+            ring.step(q, c, pj, seed, bx);
+            if (t >= K - 1) {  // the first k-1 steps only fill the ring
+                float a4[4], e4[4], sp[8], ey[8];
+                *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
+                *reinterpret_cast<float4 *>(e4) = *reinterpret_cast<const float4 *>(S + G::OFF_EX2 + 4 * wg);
+                *reinterpret_cast<float4 *>(&sp[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx);
+                *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
+                *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
+                *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
+                const bool row_ok = !EDGE || t - (K - 1) < rows;
+                unsigned long long key[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v[4];
+                    float bv = -INFINITY;
+                    int bs = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int di = i - j + 3;  // projector column w_i - s_j, relative to w0 - s0 - 3
+                        const float exy = fmaf(-a4[i], sp[di], bx[i][j]);                 // box already holds + eps
+                        const float val = exy * rsqrt_fast(fmaf(e4[i], ey[di], kEps));    // reference kernel.cu:71
+                        if (!EDGE) {
+                            v[j] = val;
+                            if (WTA && val >= bv) { bv = val; bs = s0 + j; }
+                        } else {
+                            const int d = w0 + i - (s0 + j);
+                            const bool valid = d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
+                            v[j] = valid ? val : kInvalid;
+                            if (WTA && valid && val >= bv) { bv = val; bs = s0 + j; }
+                        }
+                    }
+                    if (COST) {
+                        if (!EDGE) {
+                            __stcs(reinterpret_cast<float4 *>(out + (int64_t)i * C), make_float4(v[0], v[1], v[2], v[3]));
+                        } else if (row_ok && w0 + i < p.W) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int s = s0 + j, d = w0 + i - s;
+                                if (p.banded) {
+                                    if (s < p.D) __stcs(out + (int64_t)i * C + s, v[j]);
+                                } else if (d >= 0 && d < p.W) {
+                                    __stcs(out + (int64_t)i * C + d, v[j]);
+                                }
+                            }
+                        }
+                    }
+                    if (WTA)
+                        key[i] = bv > -INFINITY
+                                     ? ((unsigned long long)float_to_ordered(bv) << 32) | (uint32_t)(bs + p.W)
+                                     : 0ull;
+                }
+                if (WTA) {
+                    // reduce the 4 keys over the 16 lanes of the unit (reduce-scatter: 5 exchanges instead of 16)
+                    const bool hi8 = l16 & 8, hi4 = l16 & 4;
+                    unsigned long long k0 = hi8 ? key[2] : key[0], k1 = hi8 ? key[3] : key[1];
+                    k0 = max_u64(k0, shfl_xor_u64(hi8 ? key[0] : key[2], 8));
+                    k1 = max_u64(k1, shfl_xor_u64(hi8 ? key[1] : key[3], 8));
+                    unsigned long long kk = max_u64(hi4 ? k1 : k0, shfl_xor_u64(hi4 ? k0 : k1, 4));
+                    kk = max_u64(kk, shfl_xor_u64(kk, 2));
+                    kk = max_u64(kk, shfl_xor_u64(kk, 1));
+                    const int i = (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
+                    if ((l16 & 3) == 0 && kk != 0ull && (!EDGE || (row_ok && w0 + i < p.W))) atomicMax(keys + i, kk);
+                }
+            }
+            if (COST) out += out_row;
+            if (WTA) keys += p.W;
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
+        }
+    }
 }
+
+// best / index from the packed keys
+__global__ void __launch_bounds__(256)
+    wta_decode_kernel(Problem p, const unsigned long long *__restrict__ keys, float *__restrict__ best,
+                      int32_t *__restrict__ index) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.pixels()) return;
+    const unsigned long long key = keys[pix];
+    const int s = (int)(uint32_t)(key & 0xffffffffu) - p.W;
+    best[pix] = ordered_to_float((uint32_t)(key >> 32));
+    index[pix] = p.banded ? s : (int)(pix % p.W) - s;
+}
+
+template <int K, int NU, int WG, bool COST, bool WTA>
+static int launch_one(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
+                      unsigned long long *keys, cudaStream_t stream) {
+    const size_t smem = (size_t)kSlidingStages * SlideGeom<K, NU, WG>::SLOT * sizeof(float);
+    const int threads = 16 * NU * WG;
+    auto kern = sliding_forward_kernel<K, NU, WG, COST, WTA>;
+    CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
+    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys);
+    CUSTMA_LAUNCH_CHECK("sliding_forward_kernel");
+    return CUSTMA_OK;
+}
+
+template <int K, int NU, int WG>
+static int launch_cfg(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
+                      unsigned long long *keys, cudaStream_t stream) {
+    if (cost && keys) return launch_one<K, NU, WG, true, true>(p, L, ws, cost, keys, stream);
+    if (cost) return launch_one<K, NU, WG, true, false>(p, L, ws, cost, keys, stream);
+    return launch_one<K, NU, WG, false, true>(p, L, ws, cost, keys, stream);
+}
+
+template <int K>
+static int launch_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
+                    unsigned long long *keys, cudaStream_t stream) {
+    switch (cfg.NU) {
+        case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, stream);
+        case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, stream);
+        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, stream);
+        default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, stream);
+    }
+}
+
+bool sliding_forward_supported(const Problem &p) {
+    SlidingConfig cfg;
+    return sliding_pick_config(p, &cfg);
+}
+
+size_t sliding_forward_workspace_bytes(const Problem &p) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, &cfg)) return 0;
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, false, &L);
+    return L.total;
+}
+
+int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
+                           int32_t *index, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, false, &L);
+    if (workspace_bytes < L.total)
+        return set_error(CUSTMA_ERR_WORKSPACE, "sliding forward needs %zu workspace bytes, %zu given", L.total, workspace_bytes);
+    char *ws = (char *)workspace;
+    int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
+    if (rc) return rc;
+    unsigned long long *keys = best ? (unsigned long long *)(ws + L.off_wta) : nullptr;
+    rc = launch_k<5>(cfg, p, L, ws, cost, keys, stream);
+    if (rc) return rc;
+    if (best) {
+        wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index);
+        CUSTMA_LAUNCH_CHECK("wta_decode_kernel");
+    }
+    return CUSTMA_OK;
+}
+
+}  // namespace custma
