@@ -41,7 +41,7 @@ struct BwdGeom {
 // extra workspace of the backward, after the forward-style arrays (SlidingLayout::off_extra)
 struct BwdLayout {
     int32_t TW, TH;              // T1 tile: TH = RBH rows x TW columns
-    size_t off_T1, off_Am, off_Bs, total;
+    size_t off_T1, off_Am, off_Bs, off_patch, total;
 };
 
 static void make_bwd_layout(const Problem &p, const SlidingLayout &L, BwdLayout *BL) {
@@ -54,6 +54,7 @@ static void make_bwd_layout(const Problem &p, const SlidingLayout &L, BwdLayout 
     const size_t rows = (size_t)p.B * L.n_chunks * L.NB * L.RB;
     BL->off_Am = take(rows * L.cs_pitch * sizeof(float));
     BL->off_Bs = take(rows * L.cs_pitch * sizeof(float));
+    BL->off_patch = take((size_t)p.pixels() * p.k * p.k * sizeof(float));   // patch gradients of the flagged tiles
     BL->total = off;
 }
 
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     const int rows = min(L.RB, p.H - h0);
     // row steps: RBH to run every image row through the window ring + k-1 to flush the vertical ring of a
     const int steps = (L.RBH + K - 1 + F::PERIOD - 1) / F::PERIOD * F::PERIOD;
+    // ill-conditioned tiles belong to the direct two-pass kernels (sliding_fallback.cu)
+    if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) return;
 
     if (tid == 0) {
 #pragma unroll
@@ -395,6 +398,8 @@ __global__ void __launch_bounds__(256)
     const float *T1 = (const float *)(ws + BL.off_T1);
     const float *Am = (const float *)(ws + BL.off_Am), *Bs = (const float *)(ws + BL.off_Bs);
     const float *A = (const float *)(ws + L.off_A), *camP = (const float *)(ws + L.off_camP);
+    const float *patch = (const float *)(ws + BL.off_patch);
+    const uint8_t *flags = (const uint8_t *)(ws + L.off_flags), *tileany = (const uint8_t *)(ws + L.off_tileany);
     float acc = 0.f;
     // T1 tiles: band nb covers target rows [nb*RB - r, nb*RB + RBH - r), tile wt covers columns [wt*WTC - r, wt*WTC + TW - r)
     for (int nb = max(0, (y + r - L.RBH + 1) / L.RB); nb < L.NB && nb * L.RB - r <= y; ++nb) {
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__(256)
             const int tx = x - (wt * L.WTC - r);
             if (tx < 0 || tx >= BL.TW) continue;
             for (int ch = 0; ch < L.n_chunks; ++ch) {
-                const int64_t tile = (((int64_t)b * L.NB + nb) * L.n_wtiles + wt) * L.n_chunks + ch;
-                acc += T1[(tile * BL.TH + ty) * BL.TW + tx];
+                const int64_t tile = tile_index(L, b, nb, wt, ch);
+                if (!flags[tile]) acc += T1[(tile * BL.TH + ty) * BL.TW + tx];
             }
         }
     }
@@ -419,13 +424,17 @@ __global__ void __launch_bounds__(256)
             const int w = x - j + r;
             if (w < 0 || w >= p.W) continue;
             const float av = A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w];
+            const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + w / L.WTC;
             float am = 0.f, bs = 0.f;
             for (int ch = 0; ch < L.n_chunks; ++ch) {
+                if (flags[t3 * L.n_chunks + ch]) continue;
                 const int64_t o = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h) * L.cs_pitch + w;
                 am += Am[o];
                 bs += Bs[o];
             }
             sub += fmaf(bs, cv - av, am);
+            // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178, as a gather)
+            if (tileany[t3]) sub -= patch[(((int64_t)b * p.H + h) * p.W + w) * (K * K) + i * K + j];
         }
     }
     camera_grad[pix] = acc - sub;
@@ -478,6 +487,7 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
         default: rc = launch_bwd_cfg<5, 4, 3>(p, L, BL, ws, grad, stream); break;
     }
     if (rc) return rc;
+    if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;
     sliding_backward_finalize_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, L, BL, ws, camera_grad);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;

@@ -46,7 +46,15 @@ struct SlidingLayout {
     int32_t seg_cam, seg_proj, seg_cs, seg_ps, slot_floats;
     // byte offsets into the workspace
     size_t off_minmax, off_camP, off_projP, off_A, off_ex2, off_Sp, off_ey2, off_wta, off_extra, total;
+    // conditioning summaries per (pair, band, block of 16 columns) and the per-tile verdicts derived from them
+    int32_t nblk_camP, nblk_projP, nblk_cs, nblk_ps;
+    size_t off_maxabs_c, off_maxabs_p, off_e2min_c, off_e2min_p, off_flags, off_tileany, zero_end, big_end;
 };
+
+// flags[tile] != 0: the tile is ill-conditioned for the O(1) window sums and is computed by the direct kernels
+__host__ __device__ inline int64_t tile_index(const SlidingLayout &L, int b, int nb, int wt, int ch) {
+    return (((int64_t)b * L.NB + nb) * L.n_wtiles + wt) * L.n_chunks + ch;
+}
 
 __host__ __device__ inline int round_down4(int v) { return v & ~3; }  // two's complement: also right for negatives
 
@@ -249,5 +257,10 @@ bool sliding_pick_config(const Problem &p, SlidingConfig *cfg);
 void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backward, SlidingLayout *L);
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
                         cudaStream_t stream);
+// sliding_fallback.cu: the flagged tiles, cell by cell in the reference's arithmetic
+int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
+                            const char *ws, float *cost, unsigned long long *keys, cudaStream_t stream);
+int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
+                               const float *proj, const char *ws, float *patch_grad, cudaStream_t stream);
 
 }  // namespace custma

@@ -1,0 +1,195 @@
+// Fallback of the sliding-window path: the tiles that tile_flags_kernel (sliding_prep.cu) judged ill-conditioned for
+// the O(1) window sums are computed here cell by cell with centred two-pass sums, i.e. the arithmetic of the
+// reference kernels (custma/src/stereo_matching_kernel.cu:39-71 forward, :96-151 backward).  One warp per camera
+// pixel; every cell recomputes its projector window mean and moments, as the reference does.  Slow by design: it
+// only runs where the fast path would lose accuracy (flat or very low-contrast regions, borders of images with a
+// large DC level), and it returns at once for tiles without a flagged chunk.
+#include <algorithm>
+
+#include "sliding_common.cuh"
+
+namespace custma {
+
+constexpr int kFbWarps = 8;
+
+// chunk of the sliding tiling that owns cell (w, c) of column tile w_base
+__device__ __forceinline__ int cell_chunk(const Problem &p, const SlidingLayout &L, int w_base, int w, int c) {
+    const int s = p.banded ? c : w - c;
+    return (s - chunk_s_base(L, p.W, w_base, 0)) / L.SC;
+}
+
+// centred camera patch of pixel (h,w) into shared memory, returns (via all lanes) its second moment
+__device__ __forceinline__ float warp_camera_patch(const Problem &p, const float *cam_plane, int h, int w, float *camc) {
+    const int lane = threadIdx.x & 31, kk = p.k * p.k;
+    float sum = 0.f;
+    for (int t = lane; t < kk; t += 32) {
+        const float v = query_ij(cam_plane, p.H, p.W, h + t / p.k - p.r, w + t % p.k - p.r);
+        camc[t] = v;
+        sum += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float cm = sum / (float)kk;
+    float e2 = 0.f;
+    for (int t = lane; t < kk; t += 32) {
+        const float c = camc[t] - cm;
+        camc[t] = c;
+        e2 = fmaf(c, c, e2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    __syncwarp();
+    return e2;
+}
+
+// projector window of column d: mean, then centred moments against the camera patch (reference :40-70)
+__device__ __forceinline__ void cell_moments(const Problem &p, const float *proj_plane, const float *camc, int h, int d,
+                                             float *pm_out, float *exy_out, float *ey2_out) {
+    float pm = 0.f;
+    for (int i = 0; i < p.k; ++i)
+        for (int j = 0; j < p.k; ++j) pm += query_ij(proj_plane, p.H, p.W, h + i - p.r, d + j - p.r);
+    pm /= (float)(p.k * p.k);
+    float exy = 0.f, ey2 = 0.f;
+    for (int i = 0; i < p.k; ++i)
+        for (int j = 0; j < p.k; ++j) {
+            const float q = query_ij(proj_plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm;
+            exy = fmaf(camc[i * p.k + j], q, exy);
+            ey2 = fmaf(q, q, ey2);
+        }
+    *pm_out = pm; *exy_out = exy; *ey2_out = ey2;
+}
+
+__global__ void __launch_bounds__(kFbWarps * 32)
+    fallback_forward_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ cam,
+                            const float *__restrict__ proj, const uint8_t *__restrict__ flags,
+                            const uint8_t *__restrict__ tileany, float *__restrict__ cost,
+                            unsigned long long *__restrict__ keys) {
+    extern __shared__ float smem[];
+    const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
+    const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + wt;
+    if (!tileany[t3]) return;
+    const uint8_t *fl = flags + t3 * L.n_chunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = nb * L.RB, w_base = wt * L.WTC;
+    const int rows = min(L.RB, p.H - h0), cols = min(L.WTC, p.W - w_base);
+    const float *cam_plane = cam + (int64_t)b * p.H * p.W, *proj_plane = proj + (int64_t)b * p.H * p.W;
+    float *camc = smem + warp * p.k * p.k;
+    for (int pi = warp; pi < rows * cols; pi += kFbWarps) {
+        const int h = h0 + pi / cols, w = w_base + pi % cols;
+        const int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+        __syncwarp();
+        const float ex2 = warp_camera_patch(p, cam_plane, h, w, camc);
+        float bv = -INFINITY;
+        int bs = 0;
+        for (int c = lane; c < p.C; c += 32) {
+            if (!fl[cell_chunk(p, L, w_base, w, c)]) continue;
+            const int d = p.banded ? w - c : c;
+            float v = kInvalid;
+            if (d >= 0) {
+                float pm, exy, ey2;
+                cell_moments(p, proj_plane, camc, h, d, &pm, &exy, &ey2);
+                v = (exy + kEps) / sqrtf(fmaf(ex2, ey2, kEps));   // reference :71
+                const int s = w - d;
+                if (v > bv || (v == bv && s > bs)) { bv = v; bs = s; }
+            }
+            if (cost) cost[pix * p.C + c] = v;
+        }
+        if (keys) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (ov > bv || (ov == bv && os > bs)) { bv = ov; bs = os; }
+            }
+            if (lane == 0 && bv > -INFINITY)
+                atomicMax(keys + pix, ((unsigned long long)float_to_ordered(bv) << 32) | (uint32_t)(bs + p.W));
+        }
+    }
+}
+
+// patch gradient (k*k values per pixel) of the flagged cells; layout and formula of direct_patch_grad_kernel
+__global__ void __launch_bounds__(kFbWarps * 32)
+    fallback_patch_grad_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ grad,
+                               const float *__restrict__ cam, const float *__restrict__ proj,
+                               const uint8_t *__restrict__ flags, const uint8_t *__restrict__ tileany,
+                               float *__restrict__ patch_grad) {
+    extern __shared__ float smem[];
+    const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
+    const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + wt;
+    if (!tileany[t3]) return;
+    const uint8_t *fl = flags + t3 * L.n_chunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kk = p.k * p.k;
+    const int h0 = nb * L.RB, w_base = wt * L.WTC;
+    const int rows = min(L.RB, p.H - h0), cols = min(L.WTC, p.W - w_base);
+    const float *cam_plane = cam + (int64_t)b * p.H * p.W, *proj_plane = proj + (int64_t)b * p.H * p.W;
+    float *camc = smem + (size_t)warp * (kk + 2 * p.C);
+    float *a_s = camc + kk, *pm_s = a_s + p.C;
+    for (int pi = warp; pi < rows * cols; pi += kFbWarps) {
+        const int h = h0 + pi / cols, w = w_base + pi % cols;
+        const int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+        __syncwarp();
+        const float ex2 = warp_camera_patch(p, cam_plane, h, w, camc);
+        float bsum = 0.f;
+        for (int c = lane; c < p.C; c += 32) {
+            const int d = p.banded ? w - c : c;
+            float a = 0.f, pm = 0.f;
+            if (d >= 0 && fl[cell_chunk(p, L, w_base, w, c)]) {
+                float exy, ey2;
+                cell_moments(p, proj_plane, camc, h, d, &pm, &exy, &ey2);
+                const float den = sqrtf(fmaf(ex2, ey2, kEps));
+                const float g = grad[pix * p.C + c];
+                a = g / den;                                          // reference :135,:145
+                bsum += g * ey2 * (exy + kEps) / (den * den * den);   // reference :147
+            }
+            a_s[c] = a;
+            pm_s[c] = pm;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+        __syncwarp();
+        for (int t = 0; t < kk; ++t) {
+            const int y = h + t / p.k - p.r, xo = t % p.k - p.r;
+            const bool yin = y >= 0 && y < p.H;
+            const float *prow = proj_plane + (int64_t)y * p.W;
+            float acc = 0.f;
+            for (int c = lane; c < p.C; c += 32) {
+                const float a = a_s[c];
+                if (a != 0.f) {
+                    const int x = (p.banded ? w - c : c) + xo;
+                    acc = fmaf(a, ((yin && x >= 0 && x < p.W) ? __ldg(prow + x) : 0.f) - pm_s[c], acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) patch_grad[pix * kk + t] = acc - bsum * camc[t];
+        }
+    }
+}
+
+int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
+                            const char *ws, float *cost, unsigned long long *keys, cudaStream_t stream) {
+    dim3 grid(L.n_wtiles, L.NB, p.B);
+    const size_t smem = (size_t)kFbWarps * p.k * p.k * sizeof(float);
+    fallback_forward_kernel<<<grid, kFbWarps * 32, smem, stream>>>(p, L, cam, proj, (const uint8_t *)(ws + L.off_flags),
+                                                                   (const uint8_t *)(ws + L.off_tileany), cost, keys);
+    CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
+    return CUSTMA_OK;
+}
+
+size_t fallback_backward_smem(const Problem &p) { return (size_t)kFbWarps * (p.k * p.k + 2 * p.C) * sizeof(float); }
+
+int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
+                               const float *proj, const char *ws, float *patch_grad, cudaStream_t stream) {
+    dim3 grid(L.n_wtiles, L.NB, p.B);
+    const size_t smem = fallback_backward_smem(p);
+    if (smem > 200 * 1024)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback backward: last axis %d too long for shared memory", p.C);
+    CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(fallback_patch_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)std::max<size_t>(smem, 48 * 1024)));
+    fallback_patch_grad_kernel<<<grid, kFbWarps * 32, smem, stream>>>(
+        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany), patch_grad);
+    CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");
+    return CUSTMA_OK;
+}
+
+}  // namespace custma

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     const int rows = min(L.RB, p.H - h0);
     // row steps, padded to whole periods of the pair-sum ring (the band copies and statistics rows cover the padding)
     const int steps = (rows + K - 1 + G::PERIOD - 1) / G::PERIOD * G::PERIOD;
+    // ill-conditioned tiles belong to the direct two-pass kernels (sliding_fallback.cu)
+    if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) return;
 
     if (tid == 0) {
 #pragma unroll
@@ -254,6 +256,7 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
     unsigned long long *keys = best ? (unsigned long long *)(ws + L.off_wta) : nullptr;
     rc = launch_k<5>(cfg, p, L, ws, cost, keys, stream);
     if (rc) return rc;
+    if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, stream))) return rc;
     if (best) {
         wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index);
         CUSTMA_LAUNCH_CHECK("wta_decode_kernel");

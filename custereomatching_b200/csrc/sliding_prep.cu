@@ -66,8 +66,20 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     const size_t bands = (size_t)p.B * L->NB, rows = (size_t)p.B * L->NB * L->RB;
+    L->nblk_camP = (L->cam_pitch + 15) / 16; L->nblk_projP = (L->proj_pitch + 15) / 16;
+    L->nblk_cs = (L->cs_pitch + 15) / 16; L->nblk_ps = (L->ps_pitch + 15) / 16;
+    // zero-initialised region (one memset): band min/max accumulators, WTA keys, max |pivoted value| per block
     L->off_minmax = take(2 * bands * 2 * sizeof(uint32_t));            // [img][pair*band][max(v), max(-v)] ordered
-    L->off_wta = take((size_t)p.pixels() * sizeof(unsigned long long));  // packed (best, s) keys; memset with minmax
+    L->off_wta = take((size_t)p.pixels() * sizeof(unsigned long long));  // packed (best, s) keys
+    L->off_maxabs_c = take(bands * L->nblk_camP * sizeof(float));
+    L->off_maxabs_p = take(bands * L->nblk_projP * sizeof(float));
+    L->zero_end = off;
+    // "huge"-initialised region (memset 0x7f): min second moment per block
+    L->off_e2min_c = take(bands * L->nblk_cs * sizeof(float));
+    L->off_e2min_p = take(bands * L->nblk_ps * sizeof(float));
+    L->big_end = off;
+    L->off_flags = take((size_t)p.B * L->NB * L->n_wtiles * L->n_chunks);
+    L->off_tileany = take((size_t)p.B * L->NB * L->n_wtiles);
     L->off_camP = take(bands * L->RBH * L->cam_pitch * sizeof(float));
     L->off_projP = take(bands * L->RBH * L->proj_pitch * sizeof(float));
     L->off_A = take(rows * L->cs_pitch * sizeof(float));
@@ -114,10 +126,11 @@ __device__ __forceinline__ float band_pivot(const uint32_t *__restrict__ minmax,
     return isfinite(pv) ? pv : 0.f;
 }
 
-// one thread per element of the two band copies
+// four consecutive elements of the two band copies per thread; also max |pivoted value| per block of 16 columns
 __global__ void __launch_bounds__(256)
     band_copy_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
-                     const uint32_t *__restrict__ minmax, float *__restrict__ camP, float *__restrict__ projP) {
+                     const uint32_t *__restrict__ minmax, float *__restrict__ camP, float *__restrict__ projP,
+                     float *__restrict__ maxabs_c, float *__restrict__ maxabs_p) {
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B;
     const int pitch = img ? L.proj_pitch : L.cam_pitch, left = img ? L.proj_lp : L.cam_lc;
     const int t = blockIdx.y % L.RBH, nb = blockIdx.y / L.RBH;
@@ -125,51 +138,124 @@ __global__ void __launch_bounds__(256)
     const float pv = band_pivot(minmax, p, L, img, b, nb);
     const float *row = (img ? proj : cam) + ((int64_t)b * p.H + y) * p.W;
     float *out = (img ? projP : camP) + (((int64_t)b * L.NB + nb) * L.RBH + t) * pitch;
+    float *mx = (img ? maxabs_p : maxabs_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_projP : L.nblk_camP);
     const bool yin = y >= 0 && y < p.H;
-    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < pitch; ci += gridDim.x * blockDim.x) {
-        const int x = ci - left;
-        const float v = (yin && x >= 0 && x < p.W) ? __ldg(row + x) : 0.f;
-        out[ci] = v - pv;
+    const int ci = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    float m = 0.f;
+    if (ci < pitch) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int x = ci + e - left;
+            v[e] = ((yin && x >= 0 && x < p.W) ? __ldg(row + x) : 0.f) - pv;
+            m = fmaxf(m, fabsf(v[e]));
+        }
+        *reinterpret_cast<float4 *>(out + ci) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    if ((threadIdx.x & 3) == 0 && ci < pitch) atomicMax(reinterpret_cast<uint32_t *>(mx + ci / 16), __float_as_uint(m));
+}
+
+// Window statistics of the pivoted band copies: one thread per column marches down the band keeping the last k-1
+// horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  One-pass second moment
+// e2 = sum v^2 - (sum v)^2 / n on band-pivoted data: its error, eps * n * max|v|^2, is what the tile verdict bounds.
+// camera: A = window mean, ex2;   projector: Sp = window sum, ey2;   plus min e2 per block of 16 columns.
+template <int K>
+__global__ void __launch_bounds__(128)
+    band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ camP, const float *__restrict__ projP,
+                      float *__restrict__ A, float *__restrict__ ex2, float *__restrict__ Sp,
+                      float *__restrict__ ey2, float *__restrict__ e2min_c, float *__restrict__ e2min_p) {
+    const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y;
+    const int pitch = img ? L.ps_pitch : L.cs_pitch, left = img ? L.ps_ld : 0;
+    const int pitchP = img ? L.proj_pitch : L.cam_pitch, leftP = img ? L.proj_lp : L.cam_lc;
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = ci - left;
+    const bool col_ok = ci < pitch && x >= 0 && x < p.W;
+    const float *src = (img ? projP : camP) + ((int64_t)b * L.NB + nb) * L.RBH * pitchP + (col_ok ? x - L.r + leftP : 0);
+    float *o1 = (img ? Sp : A) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
+    float *o2 = (img ? ey2 : ex2) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
+    const float inv_n = 1.f / (float)(K * K);
+    float r1[K - 1], r2[K - 1];
+#pragma unroll
+    for (int m = 0; m < K - 1; ++m) r1[m] = r2[m] = 0.f;
+    float emin = 3.0e38f;
+    for (int t = 0; t < L.RBH; ++t) {
+        float h1 = 0.f, h2 = 0.f;
+        if (col_ok) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float v = src[(int64_t)t * pitchP + j];
+                h1 += v;
+                h2 = fmaf(v, v, h2);
+            }
+        }
+        float s1 = h1, s2 = h2;
+#pragma unroll
+        for (int m = 0; m < K - 1; ++m) { s1 += r1[m]; s2 += r2[m]; }
+#pragma unroll
+        for (int m = 0; m < K - 2; ++m) { r1[m] = r1[m + 1]; r2[m] = r2[m + 1]; }
+        r1[K - 2] = h1; r2[K - 2] = h2;
+        const int hr = t - (K - 1);
+        if (hr >= 0 && ci < pitch) {
+            const bool ok = col_ok && nb * L.RB + hr < p.H;
+            const float mean = s1 * inv_n;
+            const float e2 = fmaxf(fmaf(-s1, mean, s2), 0.f);
+            // neutral values elsewhere: they only ever meet masked cells
+            o1[(int64_t)hr * pitch] = ok ? (img ? s1 : mean) : 0.f;
+            o2[(int64_t)hr * pitch] = ok ? e2 : 1.f;
+            if (ok) emin = fminf(emin, e2);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+    if ((threadIdx.x & 15) == 0 && ci < pitch) {
+        float *mn = (img ? e2min_p : e2min_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_ps : L.nblk_cs) + ci / 16;
+        atomicMin(reinterpret_cast<uint32_t *>(mn), __float_as_uint(emin));   // non-negative floats order like uints
     }
 }
 
-// one thread per element of the statistics rows (camera: A, ex2; projector: Sp, ey2)
-__global__ void __launch_bounds__(256)
-    band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
-                      const uint32_t *__restrict__ minmax, float *__restrict__ A, float *__restrict__ ex2,
-                      float *__restrict__ Sp, float *__restrict__ ey2) {
-    const int img = blockIdx.z / p.B, b = blockIdx.z % p.B;
-    const int pitch = img ? L.ps_pitch : L.cs_pitch, left = img ? L.ps_ld : 0;
-    const int h = blockIdx.y, nb = h / L.RB;   // h in [0, NB*RB): rows past H are filled with neutral values
-    const float pv = band_pivot(minmax, p, L, img, b, nb);
-    const float *plane = (img ? proj : cam) + (int64_t)b * p.H * p.W;
-    const int64_t orow = ((int64_t)b * L.NB * L.RB + h) * pitch;
-    const int k = p.k, r = p.r;
-    const float inv_n = 1.f / (float)(k * k);
-    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < pitch; ci += gridDim.x * blockDim.x) {
-        const int x = ci - left;
-        float sum = 0.f, e2 = 1.f, mean = 0.f;
-        if (h < p.H && x >= 0 && x < p.W) {
-            for (int i = 0; i < k; ++i)
-                for (int j = 0; j < k; ++j) sum += query_ij(plane, p.H, p.W, h + i - r, x + j - r) - pv;
-            mean = sum * inv_n;
-            e2 = 0.f;
-            for (int i = 0; i < k; ++i)
-                for (int j = 0; j < k; ++j) {
-                    const float c = (query_ij(plane, p.H, p.W, h + i - r, x + j - r) - pv) - mean;
-                    e2 = fmaf(c, c, e2);
-                }
-        }
-        if (img) { Sp[orow + ci] = sum; ey2[orow + ci] = e2; }
-        else { A[orow + ci] = mean; ex2[orow + ci] = e2; }
+// Verdict per tile: is the fp32 error of the raw window sums, eps * n * max|cam'| * max|proj'| (and the same for the
+// one-pass second moments), safely below 1e-5 of the normalisation sqrt(ex2 * ey2 + eps) everywhere in the tile?
+// Tiles that fail (low contrast against the band pivot, image borders of images with a large DC level, ...) are left
+// to the direct two-pass kernels, which follow the reference's arithmetic order.
+__global__ void __launch_bounds__(128)
+    tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ maxabs_c,
+                      const float *__restrict__ maxabs_p, const float *__restrict__ e2min_c,
+                      const float *__restrict__ e2min_p, uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
+    if (id >= ntiles) return;
+    const int wt = (int)(id % L.n_wtiles), nb = (int)((id / L.n_wtiles) % L.NB), b = (int)(id / ((int64_t)L.n_wtiles * L.NB));
+    const int64_t band = (int64_t)b * L.NB + nb;
+    const int w_base = wt * L.WTC;
+    auto range_max = [](const float *a, int lo, int hi) { float m = 0.f; for (int i = lo / 16; i <= (hi - 1) / 16; ++i) m = fmaxf(m, a[i]); return m; };
+    auto range_min = [](const float *a, int lo, int hi) { float m = 3.0e38f; for (int i = lo / 16; i <= (hi - 1) / 16; ++i) m = fminf(m, a[i]); return m; };
+    const float cm = range_max(maxabs_c + band * L.nblk_camP, w_base - L.r + L.cam_lc, w_base - L.r + L.cam_lc + L.seg_cam);
+    const float e2c = range_min(e2min_c + band * L.nblk_cs, w_base, w_base + L.WTC);
+    const float coef = 6.0e-8f * 3.f * (float)(p.k * p.k);
+    uint8_t any = 0;
+    for (int ch = 0; ch < L.n_chunks; ++ch) {
+        const int s_base = chunk_s_base(L, p.W, w_base, ch);
+        const int xlo = w_base - L.r - s_base - L.SC + 1, dlo = w_base - s_base - L.SC + 1;
+        const float pm = range_max(maxabs_p + band * L.nblk_projP, xlo + L.proj_lp, xlo + L.proj_lp + L.seg_proj);
+        const float e2p = range_min(e2min_p + band * L.nblk_ps, dlo + L.ps_ld, dlo + L.ps_ld + L.seg_ps);
+        const bool fast = coef * cm * pm <= 3.0e-6f * sqrtf(e2c * e2p + kEps) && coef * cm * cm <= 6.0e-6f * e2c &&
+                          coef * pm * pm <= 6.0e-6f * e2p;
+        flags[id * L.n_chunks + ch] = fast ? 0 : 1;
+        any |= fast ? 0 : 1;
     }
+    tileany[id] = any;
 }
 
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
                         cudaStream_t stream) {
     uint32_t *minmax = (uint32_t *)(ws + L.off_minmax);
-    // min/max accumulators and WTA keys are adjacent: one memset
-    CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.off_minmax, 0, L.off_camP - L.off_minmax, stream));
+    float *camP = (float *)(ws + L.off_camP), *projP = (float *)(ws + L.off_projP);
+    float *maxabs_c = (float *)(ws + L.off_maxabs_c), *maxabs_p = (float *)(ws + L.off_maxabs_p);
+    float *e2min_c = (float *)(ws + L.off_e2min_c), *e2min_p = (float *)(ws + L.off_e2min_p);
+    CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.off_minmax, 0, L.zero_end - L.off_minmax, stream));
+    CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_end, 0x7f, L.big_end - L.zero_end, stream));
     {
         const int64_t n = (int64_t)L.RBH * p.W;
         dim3 grid((unsigned)std::min<int64_t>((n + 1023) / 1024, 64), L.NB, 2 * p.B);
@@ -177,17 +263,22 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
         CUSTMA_LAUNCH_CHECK("band_minmax_kernel");
     }
     {
-        dim3 grid((std::max(L.cam_pitch, L.proj_pitch) + 255) / 256, L.NB * L.RBH, 2 * p.B);
-        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, (float *)(ws + L.off_camP),
-                                                  (float *)(ws + L.off_projP));
+        dim3 grid((std::max(L.cam_pitch, L.proj_pitch) / 4 + 255) / 256, L.NB * L.RBH, 2 * p.B);
+        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, camP, projP, maxabs_c, maxabs_p);
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
-        dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 255) / 256, L.NB * L.RB, 2 * p.B);
-        band_stats_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, (float *)(ws + L.off_A),
-                                                   (float *)(ws + L.off_ex2), (float *)(ws + L.off_Sp),
-                                                   (float *)(ws + L.off_ey2));
+        dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB, 2 * p.B);
+        auto kern = p.k == 3 ? band_stats_kernel<3> : p.k == 5 ? band_stats_kernel<5> : band_stats_kernel<7>;
+        kern<<<grid, 128, 0, stream>>>(p, L, camP, projP, (float *)(ws + L.off_A), (float *)(ws + L.off_ex2),
+                                       (float *)(ws + L.off_Sp), (float *)(ws + L.off_ey2), e2min_c, e2min_p);
         CUSTMA_LAUNCH_CHECK("band_stats_kernel");
+    }
+    {
+        const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
+        tile_flags_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, stream>>>(
+            p, L, maxabs_c, maxabs_p, e2min_c, e2min_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany));
+        CUSTMA_LAUNCH_CHECK("tile_flags_kernel");
     }
     return CUSTMA_OK;
 }

@@ -65,3 +65,23 @@ def assert_grad_close(new, ref, tol=GRAD_TOL, what="grad", scale=None):
     err = np.abs(new - ref).max() / scale
     assert np.isfinite(new).all(), f"{what}: non-finite values"
     assert err <= tol, f"{what}: max error {err:.3e} of the gradient scale {scale:.3e} > {tol:.1e}"
+
+
+def assert_grad_close_or_nearer_truth(new, ref, truth, tol=GRAD_TOL, what="grad"):
+    """Gradient parity against the reference extension's golden output where the reference's own fp32 rounding
+    (atomics in arbitrary order, tests/golden/manifest.json bwd_run2run_maxabs) is larger than the tolerance:
+    passes if the result is within `tol` of the reference OR at least as close to the fp64 truth as the reference
+    itself is (plus `tol`).  On well-conditioned inputs the first clause decides."""
+    new = np.asarray(new, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    truth = np.asarray(truth, dtype=np.float64)
+    assert np.isfinite(new).all(), f"{what}: non-finite values"
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err_ref = np.abs(new - ref).max() / scale
+    if err_ref <= tol:
+        return
+    err_new_truth = np.abs(new - truth).max() / scale
+    err_ref_truth = np.abs(ref - truth).max() / scale
+    assert err_new_truth <= err_ref_truth + tol, (
+        f"{what}: {err_ref:.3e} of scale from the reference and {err_new_truth:.3e} from fp64 truth, while the "
+        f"reference itself is {err_ref_truth:.3e} from truth (tolerance {tol:.1e})")

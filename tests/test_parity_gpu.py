@@ -10,8 +10,8 @@ import torch
 
 import custma
 import custereomatching_b200 as cb
-from conftest import (COST_TOL, GRAD_TOL, assert_cost_close, assert_grad_close, golden_manifest, golden_small_names,
-                      load_golden)
+from conftest import (COST_TOL, GRAD_TOL, assert_cost_close, assert_grad_close, assert_grad_close_or_nearer_truth,
+                      golden_manifest, golden_small_names, load_golden)
 from oracle import ref_port
 from oracle import zncc_oracle as zo
 
@@ -44,7 +44,8 @@ def test_drop_in_forward_backward_vs_reference_golden(name):
     assert_cost_close(cv.detach().cpu().numpy(), g["cost_volume"])
     cv.backward(dev(g["cost_volume_grad"]))
     assert cam.grad.shape == cam.shape
-    assert_grad_close(cam.grad.cpu().numpy(), g["camera_grad"])
+    truth = zo.camera_grad_full_kernel_formula(g["camera"], g["projector"], g["cost_volume_grad"], k).numpy()
+    assert_grad_close_or_nearer_truth(cam.grad.cpu().numpy(), g["camera_grad"], truth)
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -58,7 +59,8 @@ def test_direct_kernels_forward_bit_exact_with_reference(name):
     assert np.array_equal(best.cpu().numpy(), tb.numpy())
     assert np.array_equal(idx.cpu().numpy().astype(np.int64), ti.numpy())
     grad = cb.backward(dev(g["cost_volume_grad"]), dev(g["camera"]), dev(g["projector"]), k, 0, flags=cb.FLAG_DIRECT)
-    assert_grad_close(grad.cpu().numpy(), g["camera_grad"])
+    truth = zo.camera_grad_full_kernel_formula(g["camera"], g["projector"], g["cost_volume_grad"], k).numpy()
+    assert_grad_close_or_nearer_truth(grad.cpu().numpy(), g["camera_grad"], truth)
 
 
 @pytest.mark.parametrize("flags", FLAGS)
@@ -172,7 +174,11 @@ def test_low_contrast_inputs_keep_parity(kind):
     gb = rng.randn(H, W, D).astype(np.float32)
     gref = ref_port.backward_banded(gb, cam, proj, k)
     grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D)
-    assert_grad_close(grad.cpu().numpy(), gref, tol=2e-5 if kind != "const" else GRAD_TOL)
+    # here the fp32 restatement of the reference is itself several 1e-5 of scale away from the exact gradient
+    # (every term is divided by a tiny den); accept 1e-5 of the fp32 reference arithmetic, or a result that is at
+    # least as close to the fp64 truth as that arithmetic is
+    truth = zo.camera_grad_banded_autograd(cam, proj, gb, D, k).numpy()
+    assert_grad_close_or_nearer_truth(grad.cpu().numpy(), gref, truth)
 
 
 def test_backward_is_deterministic():
