@@ -34,7 +34,7 @@ struct BwdGeom {
     static constexpr int SLOT = OFF_STG + 16 * UNITS;            // + one reduced value per lane of every unit
     static constexpr int CHUNKS = OFF_STG / 4, NCH = (CHUNKS + F::NCONS - 1) / F::NCONS;
     static constexpr int TW = F::WTC + K - 1;                    // columns of a T1 tile row
-    static_assert(TW <= 64 && 64 + 2 * F::WTC <= F::NCONS, "reduce_step thread ranges");
+    static_assert(TW <= 96 && 96 + 2 * F::WTC <= F::NCONS, "reduce_step thread ranges");
     static constexpr size_t SMEM_BYTES = ((size_t)F::NS * SLOT + (size_t)kGradStages * 16 * F::NCONS) * sizeof(float);
 };
 
@@ -186,9 +186,9 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                 }
                 T1tile[(int64_t)ty * G::TW + x] = acc;
             }
-        } else if (tid >= 64 && tid < 64 + 2 * F::WTC) {
+        } else if (tid >= 96 && tid < 96 + 2 * F::WTC) {
             if (ty < rows) {
-                const int idx = tid - 64, w = idx % F::WTC, which = idx / F::WTC;  // 0: Bs, 1: Am
+                const int idx = tid - 96, w = idx % F::WTC, which = idx / F::WTC;  // 0: Bs, 1: Am
                 float acc = 0.f;
 #pragma unroll
                 for (int q = 0; q < NU; ++q) acc += stg[((w >> 2) * NU + q) * 16 + 8 + 4 * which + (w & 3)];
@@ -300,13 +300,14 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                     *reinterpret_cast<float4 *>(&pt[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJT + pidx + 4 * v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    // target column xi (relative to w0 - r) is covered by cells w_i with xi - (K-1) <= i <= xi
+                    // target column xi (relative to w0 - r) is covered by the cells w_i with xi - (K-1) <= i <= xi:
+                    // a prefix sum of va[.][j] while the window is still entering the tile, a suffix sum afterwards
+                    float pre[4], suf[4];
+                    pre[0] = va[0][j]; pre[1] = pre[0] + va[1][j]; pre[2] = pre[1] + va[2][j]; pre[3] = pre[2] + va[3][j];
+                    suf[3] = va[3][j]; suf[2] = suf[3] + va[2][j]; suf[1] = suf[2] + va[1][j]; suf[0] = pre[3];
 #pragma unroll
                     for (int xi = 0; xi < K + 3; ++xi) {
-                        float h = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (i <= xi && i >= xi - (K - 1)) h += va[i][j];
+                        const float h = xi - (K - 1) <= 0 ? pre[xi < 3 ? xi : 3] : suf[xi - (K - 1)];
                         red[xi] = fmaf(pt[xi - j + 3], h, red[xi]);
                     }
                 }
@@ -340,7 +341,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 }
 
 template <int K, int NU, int WG>
-__global__ void __launch_bounds__(16 * NU * WG, 2)
+__global__ void __launch_bounds__(16 * NU * WG, 1)
     sliding_backward_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
                             const float *__restrict__ grad) {
     using F = SlideGeom<K, NU, WG>;
@@ -454,12 +455,12 @@ static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLay
 
 bool sliding_backward_supported(const Problem &p) {
     SlidingConfig cfg;
-    return sliding_pick_config(p, &cfg);
+    return sliding_pick_config(p, true, &cfg);
 }
 
 size_t sliding_backward_workspace_bytes(const Problem &p) {
     SlidingConfig cfg;
-    if (!sliding_pick_config(p, &cfg)) return 0;
+    if (!sliding_pick_config(p, true, &cfg)) return 0;
     SlidingLayout L;
     make_sliding_layout(p, cfg, true, &L);
     BwdLayout BL;
@@ -470,7 +471,7 @@ size_t sliding_backward_workspace_bytes(const Problem &p) {
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
                             float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     SlidingConfig cfg;
-    if (!sliding_pick_config(p, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
+    if (!sliding_pick_config(p, true, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
     make_sliding_layout(p, cfg, true, &L);
     BwdLayout BL;
@@ -481,10 +482,9 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
     if (rc) return rc;
     switch (cfg.NU) {
-        case 1: rc = launch_bwd_cfg<5, 1, 12>(p, L, BL, ws, grad, stream); break;
-        case 2: rc = launch_bwd_cfg<5, 2, 6>(p, L, BL, ws, grad, stream); break;
-        case 3: rc = launch_bwd_cfg<5, 3, 4>(p, L, BL, ws, grad, stream); break;
-        default: rc = launch_bwd_cfg<5, 4, 3>(p, L, BL, ws, grad, stream); break;
+        case 1: rc = launch_bwd_cfg<5, 1, 16>(p, L, BL, ws, grad, stream); break;
+        case 2: rc = launch_bwd_cfg<5, 2, 8>(p, L, BL, ws, grad, stream); break;
+        default: rc = launch_bwd_cfg<5, 4, 4>(p, L, BL, ws, grad, stream); break;
     }
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;

@@ -253,7 +253,7 @@ struct RowLoader {
 };
 
 // host side (sliding_prep.cu)
-bool sliding_pick_config(const Problem &p, SlidingConfig *cfg);
+bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg);
 void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backward, SlidingLayout *L);
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
                         cudaStream_t stream);

@@ -231,12 +231,12 @@ static int launch_k(const SlidingConfig &cfg, const Problem &p, const SlidingLay
 
 bool sliding_forward_supported(const Problem &p) {
     SlidingConfig cfg;
-    return sliding_pick_config(p, &cfg);
+    return sliding_pick_config(p, false, &cfg);
 }
 
 size_t sliding_forward_workspace_bytes(const Problem &p) {
     SlidingConfig cfg;
-    if (!sliding_pick_config(p, &cfg)) return 0;
+    if (!sliding_pick_config(p, false, &cfg)) return 0;
     SlidingLayout L;
     make_sliding_layout(p, cfg, false, &L);
     return L.total;
@@ -245,7 +245,7 @@ size_t sliding_forward_workspace_bytes(const Problem &p) {
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
                            int32_t *index, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     SlidingConfig cfg;
-    if (!sliding_pick_config(p, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
+    if (!sliding_pick_config(p, false, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
     make_sliding_layout(p, cfg, false, &L);
     if (workspace_bytes < L.total)

@@ -16,15 +16,22 @@
 
 namespace custma {
 
-bool sliding_pick_config(const Problem &p, SlidingConfig *cfg) {
+bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg) {
     if (p.k != 5) return false;
     cfg->K = p.k;
     const int span = p.banded ? p.D : p.W + 32;
-    // 6 consumer warps + 1 producer warp per CTA, two CTAs per SM (one CTA's start-up hides behind the other)
-    if (span <= 64) { cfg->NU = 1; cfg->WG = 12; }
-    else if (span <= 128) { cfg->NU = 2; cfg->WG = 6; }
-    else if (span <= 192) { cfg->NU = 3; cfg->WG = 4; }
-    else { cfg->NU = 4; cfg->WG = 3; }
+    cfg->NU = span <= 64 ? 1 : span <= 128 ? 2 : span <= 192 ? 3 : 4;
+    if (!backward) {
+        // forward: 6 warps (168 registers) per CTA, two CTAs per SM so that one CTA's start-up hides behind the other
+        const int wg[5] = {0, 12, 6, 4, 3};
+        cfg->WG = wg[cfg->NU];
+    } else {
+        // backward: two register rings per cell (window sum + vertical sum of a) need ~250 registers: one CTA of
+        // 256 threads per SM, so NU * WG = 16; 129..192 disparities run as chunks of 64 rather than wasting a
+        // quarter of a 256-wide chunk
+        if (cfg->NU == 3) cfg->NU = 1;
+        cfg->WG = 16 / cfg->NU;
+    }
     return true;
 }
 
