@@ -387,20 +387,48 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
 }
 
 // camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of
-// ( Am[h,w] + Bs[h,w] * (cam'[y,x] - A[h,w]) ), cam' and A relative to the pivot of the band of row h.
-// Fixed summation order; out-of-image cells do not exist, out-of-image targets are never computed (reference :177).
-__global__ void __launch_bounds__(256)
+// ( Am[h,w] + Bs[h,w] * (cam'[y,x] - A[h,w]) ), cam' and A relative to the pivot of the band of row h.  Written as
+// sum_h ( sum_w q1[h,w] + cam'_h[y,x] * sum_w q2[h,w] ) with q1 = Am - Bs*A, q2 = Bs staged per 32x8 pixel block in
+// shared memory.  Fixed summation order; out-of-image cells do not exist, out-of-image targets are never computed
+// (reference :177).  Cells of flagged chunks arrive as ready-made patch gradients (sliding_fallback.cu).
+constexpr int kFinTX = 32, kFinTY = 8, kFinMaxK = 7;
+
+__global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad) {
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p.pixels()) return;
-    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), b = (int)(pix / ((int64_t)p.H * p.W));
-    const int K = L.K, r = L.r;
+    __shared__ float q1[kFinTY + kFinMaxK - 1][kFinTX + kFinMaxK], q2[kFinTY + kFinMaxK - 1][kFinTX + kFinMaxK];
+    const int K = L.K, r = L.r, back = K - 1 - r;
+    const int x0 = blockIdx.x * kFinTX, y0 = blockIdx.y * kFinTY, b = blockIdx.z;
+    const int tid = threadIdx.y * kFinTX + threadIdx.x;
     const float *T1 = (const float *)(ws + BL.off_T1);
     const float *Am = (const float *)(ws + BL.off_Am), *Bs = (const float *)(ws + BL.off_Bs);
     const float *A = (const float *)(ws + L.off_A), *camP = (const float *)(ws + L.off_camP);
     const float *patch = (const float *)(ws + BL.off_patch);
     const uint8_t *flags = (const uint8_t *)(ws + L.off_flags), *tileany = (const uint8_t *)(ws + L.off_tileany);
+    const int SW = kFinTX + K - 1, SH = kFinTY + K - 1;
+    int flagged_near = 0;
+    for (int e = tid; e < SW * SH; e += kFinTX * kFinTY) {
+        const int hh = e / SW, ww = e % SW, h = y0 - back + hh, w = x0 - back + ww;
+        float v1 = 0.f, v2 = 0.f;
+        if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
+            const int64_t t3 = ((int64_t)b * L.NB + h / L.RB) * L.n_wtiles + w / L.WTC;
+            float am = 0.f, bs = 0.f;
+            for (int ch = 0; ch < L.n_chunks; ++ch) {
+                if (flags[t3 * L.n_chunks + ch]) continue;
+                const int64_t o = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h) * L.cs_pitch + w;
+                am += Am[o];
+                bs += Bs[o];
+            }
+            v1 = fmaf(-bs, A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w], am);
+            v2 = bs;
+            flagged_near |= tileany[t3];
+        }
+        q1[hh][ww] = v1;
+        q2[hh][ww] = v2;
+    }
+    flagged_near = __syncthreads_or(flagged_near);
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= p.W || y >= p.H) return;
     float acc = 0.f;
     // T1 tiles: band nb covers target rows [nb*RB - r, nb*RB + RBH - r), tile wt covers columns [wt*WTC - r, wt*WTC + TW - r)
     for (int nb = max(0, (y + r - L.RBH + 1) / L.RB); nb < L.NB && nb * L.RB - r <= y; ++nb) {
@@ -421,24 +449,23 @@ __global__ void __launch_bounds__(256)
         if (h < 0 || h >= p.H) continue;
         const int nb = h / L.RB;
         const float cv = camP[(((int64_t)b * L.NB + nb) * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
+        const int hh = threadIdx.y + K - 1 - i;
+        float s1 = 0.f, s2 = 0.f;
         for (int j = 0; j < K; ++j) {
-            const int w = x - j + r;
-            if (w < 0 || w >= p.W) continue;
-            const float av = A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w];
-            const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + w / L.WTC;
-            float am = 0.f, bs = 0.f;
-            for (int ch = 0; ch < L.n_chunks; ++ch) {
-                if (flags[t3 * L.n_chunks + ch]) continue;
-                const int64_t o = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h) * L.cs_pitch + w;
-                am += Am[o];
-                bs += Bs[o];
+            s1 += q1[hh][threadIdx.x + K - 1 - j];
+            s2 += q2[hh][threadIdx.x + K - 1 - j];
+        }
+        sub += fmaf(cv, s2, s1);
+        if (flagged_near) {
+            for (int j = 0; j < K; ++j) {
+                const int w = x - j + r;
+                if (w < 0 || w >= p.W) continue;
+                if (tileany[((int64_t)b * L.NB + nb) * L.n_wtiles + w / L.WTC])
+                    sub -= patch[(((int64_t)b * p.H + h) * p.W + w) * (K * K) + i * K + j];
             }
-            sub += fmaf(bs, cv - av, am);
-            // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178, as a gather)
-            if (tileany[t3]) sub -= patch[(((int64_t)b * p.H + h) * p.W + w) * (K * K) + i * K + j];
         }
     }
-    camera_grad[pix] = acc - sub;
+    camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc - sub;
 }
 
 template <int K, int NU, int WG>
@@ -488,7 +515,8 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     }
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;
-    sliding_backward_finalize_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, L, BL, ws, camera_grad);
+    sliding_backward_finalize_kernel<<<dim3((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B),
+                                       dim3(kFinTX, kFinTY), 0, stream>>>(p, L, BL, ws, camera_grad);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;
 }
