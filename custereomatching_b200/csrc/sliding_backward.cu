@@ -35,7 +35,11 @@ struct BwdGeom {
     static constexpr int CHUNKS = OFF_STG / 4, NCH = (CHUNKS + F::NCONS - 1) / F::NCONS;
     static constexpr int TW = F::WTC + K - 1;                    // columns of a T1 tile row
     static_assert(TW <= 96 && 96 + 2 * F::WTC <= F::NCONS, "reduce_step thread ranges");
-    static constexpr size_t SMEM_BYTES = ((size_t)F::NS * SLOT + (size_t)kGradStages * 16 * F::NCONS) * sizeof(float);
+    static constexpr int XPOSE_STRIDE = 20;                     // floats per lane row of the transpose scratch
+    // row ring | gradient ring (+ one stage that stays zero) | transpose scratch (16 lanes x 20 floats per unit)
+    static constexpr int GRAD_FLOATS = (kGradStages + 1) * 16 * F::NCONS, XPOSE_FLOATS = UNITS * 16 * XPOSE_STRIDE;
+    static constexpr int SMEM_FLOATS = F::NS * SLOT + GRAD_FLOATS + XPOSE_FLOATS;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_FLOATS * sizeof(float);
 };
 
 // extra workspace of the backward, after the forward-style arrays (SlidingLayout::off_extra)
@@ -141,7 +145,7 @@ struct SumRing {
     }
 };
 
-template <int K, int NU, int WG, bool EDGE>
+template <int K, int NU, int WG, int MODE>
 __device__ __forceinline__ void backward_consumer(const Problem &p, const SlidingLayout &L, float *smem,
                                                   uint64_t *full_bar, uint64_t *empty_bar,
                                                   BwdRowLoader<K, NU, WG> &loader, int b, int h0, int rows, int w_base,
@@ -159,8 +163,19 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     const float seed = kEps / (float)K, inv_n = 1.f / (float)(K * K);
     float *gsm = smem + NS * G::SLOT;   // [kGradStages][4][NT] float4
     // upstream gradient of (row h0, column w0, disparity s0); row hr, column i: + (hr*W + i) * C
-    const float *gsrc = grad + (((int64_t)b * p.H + h0) * p.W + w0) * C + (EDGE ? 0 : s0);
+    const float *gsrc = grad + (((int64_t)b * p.H + h0) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
+    uint32_t cmask = 0;  // MODE 1: bit 4i+j = cell (w0+i, s0+j) exists and is valid; constant over the band's rows
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (w0 + i < p.W && w0 + i - (s0 + j) >= 0) cmask |= 1u << (4 * i + j);
+    }
     const int64_t g_row = (int64_t)p.W * C;
+
+    float *xps = gsm + G::GRAD_FLOATS + u * (16 * G::XPOSE_STRIDE);   // this unit's transpose scratch
+    const float *gzero = gsm + (kGradStages * 4) * (4 * NT) + 4 * tid;  // a stage that is never written: stays zero
 
     BoxRing<K> ring;
     SumRing<K> vring;
@@ -197,6 +212,10 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
         }
     };
 
+    // The row loop is straight-line: every step runs the window ring, the cell epilogue, the vertical ring and the
+    // target-row product, also during the k-1 warm-up and k-1 flush steps.  Shared memory was zeroed at kernel start,
+    // so steps without a cell row see finite stale statistics and a zero gradient (a = bc = 0), and steps without a
+    // target row multiply zeros; no select or branch is needed in the loop body.
 #pragma unroll 1
     for (int t0 = 0; t0 < steps; t0 += PERIOD) {
 #pragma unroll
@@ -210,90 +229,85 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             }
             if (t + kLookahead < steps) loader.issue(t + kLookahead, smem, full_bar);
             // ---- prefetch the upstream gradient row that step t + kGradLookahead consumes
-            if (!EDGE) {
+            if (MODE != 2) {
                 const int hp = t + kGradLookahead - (K - 1);
                 if (hp >= 0 && hp < rows) {
                     float *gdst = gsm + ((hp & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * C);
+                    for (int i = 0; i < 4; ++i)
+                        if (MODE == 0 || w0 + i < p.W)   // columns past the image stay zero from the initial fill
+                            cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * C);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             mbar_wait(&full_bar[slot], (t / NS) & 1);
             float *S = smem + slot * G::SLOT;
-
-            float a[4][4];
-            float red[16];  // T1[0..8), Bs[0..4), Am[0..4)
-#pragma unroll
-            for (int n = 0; n < 16; ++n) red[n] = 0.f;
             const int hr = t - (K - 1);
-            if (t < L.RBH) {
-                float c[CL], pj[PL];
+            const bool has_cells = hr >= 0 && hr < rows;
+
+            float c[CL], pj[PL];
 #pragma unroll
-                for (int v = 0; v < CL / 4; ++v)
-                    *reinterpret_cast<float4 *>(&c[4 * v]) = *reinterpret_cast<const float4 *>(S + 4 * wg + 4 * v);
+            for (int v = 0; v < CL / 4; ++v)
+                *reinterpret_cast<float4 *>(&c[4 * v]) = *reinterpret_cast<const float4 *>(S + 4 * wg + 4 * v);
 #pragma unroll
-                for (int v = 0; v < PL / 4; ++v)
-                    *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
-                float bx[4][4];
-                ring.step(q, c, pj, seed, bx);
-                if (hr >= 0 && hr < rows) {
-                    float a4[4], e4[4], sp[8], ey[8], gg[4][4];
-                    *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
-                    *reinterpret_cast<float4 *>(e4) = *reinterpret_cast<const float4 *>(S + G::OFF_EX2 + 4 * wg);
-                    *reinterpret_cast<float4 *>(&sp[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx);
-                    *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
-                    *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
-                    *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
-                    if (!EDGE) {
-                        asm volatile("cp.async.wait_group %0;" ::"n"(kGradLookahead) : "memory");
-                        const float *gs = gsm + ((hr & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
+            for (int v = 0; v < PL / 4; ++v)
+                *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
+            float bx[4][4];
+            ring.step(q, c, pj, seed, bx);
+
+            float a4[4], e4[4], sp[8], ey[8], gg[4][4];
+            *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
+            *reinterpret_cast<float4 *>(e4) = *reinterpret_cast<const float4 *>(S + G::OFF_EX2 + 4 * wg);
+            *reinterpret_cast<float4 *>(&sp[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx);
+            *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
+            *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
+            *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
+            if (MODE != 2) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kGradLookahead) : "memory");
+                const float *gs = has_cells ? gsm + ((hr & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid : gzero;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int s = s0 + j, d = w0 + i - s;
-                                const bool valid = w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s < p.D);
-                                gg[i][j] = valid ? __ldg(gsrc + hr * g_row + (int64_t)i * C + (p.banded ? s : d)) : 0.f;
-                            }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float bs = 0.f, am = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int di = i - j + 3;
-                            const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
-                            const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
-                            const float av = gg[i][j] * rs;                              // a  = g / den        (:135,:145)
-                            const float bc = (av * e) * (ey[di] * (rs * rs));            // bc = g*ey2*(exy+eps)/den^3 (:147)
-                            a[i][j] = av;
-                            bs += bc;
-                            am = fmaf(av, sp[di], am);
-                        }
-                        red[8 + i] = bs;
-                        red[12 + i] = am;
-                    }
-                } else {
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
+                if (MODE == 1) {   // whatever the caller left in the invalid cells of the gradient must not leak
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+                        for (int j = 0; j < 4; ++j)
+                            if (!((cmask >> (4 * i + j)) & 1u)) gg[i][j] = 0.f;
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const int s = s0 + j, d = w0 + i - s;
+                        const bool valid = has_cells && w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s < p.D);
+                        gg[i][j] = valid ? __ldg(gsrc + hr * g_row + (int64_t)i * C + (p.banded ? s : d)) : 0.f;
+                    }
+            }
+            float a[4][4];
+            float red[16];  // T1[0..8), Bs[0..4), Am[0..4)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float bs = 0.f, am = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int di = i - j + 3;
+                    const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
+                    const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
+                    const float av = gg[i][j] * rs;                              // a  = g / den               (:135,:145)
+                    const float bc = (av * e) * (ey[di] * (rs * rs));            // bc = g*ey2*(exy+eps)/den^3 (:147)
+                    a[i][j] = av;
+                    bs = j == 0 ? bc : bs + bc;
+                    am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
+                }
+                red[8 + i] = bs;
+                red[12 + i] = am;
             }
             // ---- vertical k-row sum of a, then the target row y = hr - r:  T1[x] += proj'[y, x - s] * sum_w va[w][s]
             float va[4][4];
             vring.step(q, a, va);
-            if (t >= K - 1) {
+            {
                 float pt[PL];
 #pragma unroll
                 for (int v = 0; v < PL / 4; ++v)
@@ -308,25 +322,22 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 #pragma unroll
                     for (int xi = 0; xi < K + 3; ++xi) {
                         const float h = xi - (K - 1) <= 0 ? pre[xi < 3 ? xi : 3] : suf[xi - (K - 1)];
-                        red[xi] = fmaf(pt[xi - j + 3], h, red[xi]);
+                        red[xi] = j == 0 ? pt[xi + 3] * h : fmaf(pt[xi - j + 3], h, red[xi]);
                     }
                 }
             }
-            // ---- reduce the 16 partial sums over the 16 lanes of the unit (reduce-scatter): lane l ends with value #l
+            // ---- sum the 16 partials over the 16 lanes of the unit through a shared-memory transpose (fixed order):
+            //      lane l ends with value #l
             {
-                const bool b8 = l16 & 8, b4 = l16 & 4, b2 = l16 & 2, b1 = l16 & 1;
-                float k8[8], k4[4], k2[2];
 #pragma unroll
-                for (int n = 0; n < 8; ++n)
-                    k8[n] = (b8 ? red[n + 8] : red[n]) + __shfl_xor_sync(0xffffffffu, b8 ? red[n] : red[n + 8], 8);
+                for (int v = 0; v < 4; ++v)
+                    *reinterpret_cast<float4 *>(xps + l16 * G::XPOSE_STRIDE + 4 * v) =
+                        make_float4(red[4 * v], red[4 * v + 1], red[4 * v + 2], red[4 * v + 3]);
+                __syncwarp();
+                float tot = xps[l16];
 #pragma unroll
-                for (int n = 0; n < 4; ++n)
-                    k4[n] = (b4 ? k8[n + 4] : k8[n]) + __shfl_xor_sync(0xffffffffu, b4 ? k8[n] : k8[n + 4], 4);
-#pragma unroll
-                for (int n = 0; n < 2; ++n)
-                    k2[n] = (b2 ? k4[n + 2] : k4[n]) + __shfl_xor_sync(0xffffffffu, b2 ? k4[n] : k4[n + 2], 2);
-                const float k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k2[0] : k2[1], 1);
-                S[G::OFF_STG + u * 16 + l16] = k1;
+                for (int m = 1; m < 16; ++m) tot += xps[m * G::XPOSE_STRIDE + l16];
+                S[G::OFF_STG + u * 16 + l16] = tot;
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
@@ -366,6 +377,9 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
         }
         mbar_fence_init();
     }
+    // the row loop relies on never-loaded regions holding finite values and on one gradient stage staying zero
+    for (int i = tid; i < BwdGeom<K, NU, WG>::SMEM_FLOATS / 4; i += F::NCONS)
+        reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     BwdRowLoader<K, NU, WG> loader;
     loader.init(L, ws, b, nb, h0, w_base, s_base);
@@ -376,14 +390,17 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     const int64_t prow = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h0) * L.cs_pitch + w_base;
     float *AmRow = (float *)(ws + BL.off_Am) + prow, *BsRow = (float *)(ws + BL.off_Bs) + prow;
 
-    const bool interior = p.banded && (p.D & 3) == 0 && rows == L.RB && w_base + WTC <= p.W && s_base + SC <= p.D &&
-                          w_base - (s_base + SC - 1) >= 0;
-    if (interior)
-        backward_consumer<K, NU, WG, false>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                            grad, T1tile, AmRow, BsRow);
+    // bodies as in the forward: 0 = all cells valid, 1 = 16-byte gradient loads with a validity mask, 2 = scalar
+    const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
+    if (vec && w_base + WTC <= p.W && w_base - (s_base + SC - 1) >= 0)
+        backward_consumer<K, NU, WG, 0>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
+                                        grad, T1tile, AmRow, BsRow);
+    else if (vec)
+        backward_consumer<K, NU, WG, 1>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
+                                        grad, T1tile, AmRow, BsRow);
     else
-        backward_consumer<K, NU, WG, true>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                           grad, T1tile, AmRow, BsRow);
+        backward_consumer<K, NU, WG, 2>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
+                                        grad, T1tile, AmRow, BsRow);
 }
 
 // camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of

@@ -20,7 +20,7 @@ namespace custma {
 
 
 
-template <int K, int NU, int WG, bool EDGE, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, bool COST, bool WTA>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
@@ -58,15 +58,19 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     loader.init(L, ws, b, nb, h0, w_base, s_base);
     for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar, empty_bar);
 
-    // tiles whose every cell is a valid, 16-byte aligned store take the check-free body
-    const bool interior = p.banded && (p.D & 3) == 0 && rows == L.RB && w_base + WTC <= p.W && s_base + SC <= p.D &&
-                          w_base - (s_base + SC - 1) >= 0;
-    if (interior)
-        forward_consumer<K, NU, WG, false, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base,
-                                                      s_base, steps, cost, wta_keys);
+    // Three bodies: 0 = every cell of the tile is valid (check-free, 128-bit stores); 1 = 128-bit stores with a
+    // per-thread validity mask (tiles that touch w - s < 0 or the right image border); 2 = scalar, fully checked
+    // (reference-shaped volume, D not a multiple of the chunk).
+    const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
+    if (vec && w_base + WTC <= p.W && w_base - (s_base + SC - 1) >= 0)
+        forward_consumer<K, NU, WG, 0, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
+                                                  steps, cost, wta_keys);
+    else if (vec)
+        forward_consumer<K, NU, WG, 1, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
+                                                  steps, cost, wta_keys);
     else
-        forward_consumer<K, NU, WG, true, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base,
-                                                     s_base, steps, cost, wta_keys);
+        forward_consumer<K, NU, WG, 2, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
+                                                  steps, cost, wta_keys);
 }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -74,7 +78,7 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 __device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-template <int K, int NU, int WG, bool EDGE, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, bool COST, bool WTA>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
@@ -88,7 +92,15 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
     const int C = p.C;
     // pixel (h0 - (K-1), w0): output row of step t is h0 + t - (K-1), so the running pointers start k-1 rows early
     const int64_t pix_start = ((int64_t)b * p.H + h0 - (K - 1)) * p.W + w0;
-    float *out = COST ? cost + pix_start * C + (EDGE ? 0 : s0) : nullptr;
+    float *out = COST ? cost + pix_start * C + (MODE == 2 ? 0 : s0) : nullptr;
+    uint32_t cmask = 0;  // MODE 1: bit 4i+j = cell (w0+i, s0+j) exists and is valid; constant over the band's rows
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (w0 + i < p.W && w0 + i - (s0 + j) >= 0) cmask |= 1u << (4 * i + j);
+    }
     unsigned long long *keys = WTA ? wta_keys + pix_start : nullptr;
     const int64_t out_row = (int64_t)p.W * C;
     const float seed = kEps / (float)K;
@@ -122,7 +134,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                 *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
                 *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
                 *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
-                const bool row_ok = !EDGE || t - (K - 1) < rows;
+                const bool row_ok = t - (K - 1) < rows;   // false only in the padding steps of a short last band
                 unsigned long long key[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -134,20 +146,28 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                         const int di = i - j + 3;  // projector column w_i - s_j, relative to w0 - s0 - 3
                         const float exy = fmaf(-a4[i], sp[di], bx[i][j]);                 // box already holds + eps
                         const float val = exy * rsqrt_fast(fmaf(e4[i], ey[di], kEps));    // reference kernel.cu:71
-                        if (!EDGE) {
+                        if (MODE == 0) {
                             v[j] = val;
-                            if (WTA && val >= bv) { bv = val; bs = s0 + j; }
+                            if (WTA && (j == 0 || val >= bv)) { bv = val; bs = s0 + j; }
                         } else {
-                            const int d = w0 + i - (s0 + j);
-                            const bool valid = d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
+                            bool valid;
+                            if (MODE == 1) {
+                                valid = (cmask >> (4 * i + j)) & 1u;
+                            } else {
+                                const int d = w0 + i - (s0 + j);
+                                valid = d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
+                            }
                             v[j] = valid ? val : kInvalid;
                             if (WTA && valid && val >= bv) { bv = val; bs = s0 + j; }
                         }
                     }
-                    if (COST) {
-                        if (!EDGE) {
+                    if (COST && row_ok) {
+                        if (MODE == 0) {
                             __stcs(reinterpret_cast<float4 *>(out + (int64_t)i * C), make_float4(v[0], v[1], v[2], v[3]));
-                        } else if (row_ok && w0 + i < p.W) {
+                        } else if (MODE == 1) {
+                            if (w0 + i < p.W)
+                                __stcs(reinterpret_cast<float4 *>(out + (int64_t)i * C), make_float4(v[0], v[1], v[2], v[3]));
+                        } else if (w0 + i < p.W) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int s = s0 + j, d = w0 + i - s;
@@ -160,7 +180,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                         }
                     }
                     if (WTA)
-                        key[i] = bv > -INFINITY
+                        key[i] = (MODE == 0 || bv > -INFINITY)
                                      ? ((unsigned long long)float_to_ordered(bv) << 32) | (uint32_t)(bs + p.W)
                                      : 0ull;
                 }
@@ -174,7 +194,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                     kk = max_u64(kk, shfl_xor_u64(kk, 2));
                     kk = max_u64(kk, shfl_xor_u64(kk, 1));
                     const int i = (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
-                    if ((l16 & 3) == 0 && kk != 0ull && (!EDGE || (row_ok && w0 + i < p.W))) atomicMax(keys + i, kk);
+                    if ((l16 & 3) == 0 && row_ok && (MODE == 0 || (kk != 0ull && w0 + i < p.W))) atomicMax(keys + i, kk);
                 }
             }
             if (COST) out += out_row;
