@@ -296,9 +296,8 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                     const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
                     const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
                     const float av = gg[i][j] * rs;                              // a  = g / den               (:135,:145)
-                    const float bc = (av * e) * (ey[di] * (rs * rs));            // bc = g*ey2*(exy+eps)/den^3 (:147)
-                    a[i][j] = av;
-                    bs = j == 0 ? bc : bs + bc;
+                    a[i][j] = av;                                                // bc = g*ey2*(exy+eps)/den^3 (:147)
+                    bs = j == 0 ? (av * e) * (ey[di] * (rs * rs)) : fmaf(av * e, ey[di] * (rs * rs), bs);
                     am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
                 }
                 red[8 + i] = bs;

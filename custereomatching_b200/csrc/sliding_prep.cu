@@ -43,13 +43,20 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->banded = p.banded; L->smin_full = 0;
     L->n_wtiles = (p.W + L->WTC - 1) / L->WTC;
     L->n_chunks = p.banded ? (p.D + L->SC - 1) / L->SC : (p.W + L->WTC + 3 + L->SC - 1) / L->SC;
-    // rows per band: as large as possible (k-1 warm-up rows per band are recomputed) while one pair alone still gives
-    // about two CTAs per resident slot; independent of B, so that a batch and its pairs one by one give the same bits.
+    // Rows per band.  Every band recomputes k-1 warm-up rows (twice that in the backward), so use as few bands as
+    // possible, of equal height, while one pair alone still gives two waves of resident CTAs (forward: 2 CTAs per SM,
+    // backward: 1).  Independent of B, so that a batch and its pairs one by one give the same bits.
     // RB + K - 1 row steps must be a whole number of pair-sum-ring periods (K - 2).
     const int64_t tiles = (int64_t)L->n_wtiles * L->n_chunks;
-    auto fit = [&](int target) { return target - (target + cfg.K - 1) % (cfg.K - 2); };
-    int RB = fit(64);
-    for (int target = 48; target >= 16 && ((p.H + RB - 1) / RB) * tiles < 4 * 148; target -= 16) RB = fit(target);
+    const int64_t want = backward ? 2 * 148 : 4 * 148;
+    auto fit_up = [&](int rows) { while ((rows + cfg.K - 1) % (cfg.K - 2)) ++rows; return rows; };
+    int RB = 16;
+    for (int nbands = 1; nbands <= p.H; ++nbands) {
+        const int rb = fit_up((p.H + nbands - 1) / nbands);
+        if (rb > 128) continue;
+        RB = rb;
+        if (nbands * tiles >= want || rb <= 16) break;
+    }
     L->RB = RB; L->RBH = RB + cfg.K - 1; L->NB = (p.H + RB - 1) / RB;
     L->seg_cam = cfg.seg_cam(); L->seg_proj = cfg.seg_proj(); L->seg_cs = cfg.seg_cs(); L->seg_ps = cfg.seg_ps();
     L->slot_floats = L->seg_cam + L->seg_proj + 2 * L->seg_cs + 2 * L->seg_ps;
@@ -95,7 +102,6 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->off_Sp = take(rows * L->ps_pitch * sizeof(float));
     L->off_ey2 = take(rows * L->ps_pitch * sizeof(float));
     L->off_extra = off;
-    (void)backward;
     L->total = off;
 }
 
