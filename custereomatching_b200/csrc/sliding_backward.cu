@@ -45,6 +45,8 @@ struct BwdGeom {
 // extra workspace of the backward, after the forward-style arrays (SlidingLayout::off_extra)
 struct BwdLayout {
     int32_t TW, TH;              // T1 tile: TH = RBH rows x TW columns
+    int32_t Hp, Wp;              // T1 images: [B][n_chunks][band parity][tile parity][Hp][Wp], row y + r, column x + r;
+                                 // tiles of equal parities never overlap, so every tile stores its rows directly
     size_t off_T1, off_Am, off_Bs, off_patch, total;
 };
 
@@ -53,8 +55,9 @@ static void make_bwd_layout(const Problem &p, const SlidingLayout &L, BwdLayout 
     BL->TH = L.RBH;
     size_t off = L.off_extra;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-    const size_t tiles = (size_t)p.B * L.NB * L.n_wtiles * L.n_chunks;
-    BL->off_T1 = take(tiles * BL->TH * BL->TW * sizeof(float));
+    BL->Hp = L.NB * L.RB + L.K - 1;
+    BL->Wp = L.n_wtiles * L.WTC + L.K - 1;
+    BL->off_T1 = take((size_t)p.B * L.n_chunks * 4 * BL->Hp * BL->Wp * sizeof(float));
     const size_t rows = (size_t)p.B * L.n_chunks * L.NB * L.RB;
     BL->off_Am = take(rows * L.cs_pitch * sizeof(float));
     BL->off_Bs = take(rows * L.cs_pitch * sizeof(float));
@@ -150,8 +153,8 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                                                   uint64_t *full_bar, uint64_t *empty_bar,
                                                   BwdRowLoader<K, NU, WG> &loader, int b, int h0, int rows, int w_base,
                                                   int s_base, int steps, const float *__restrict__ grad,
-                                                  float *__restrict__ T1tile, float *__restrict__ AmRow,
-                                                  float *__restrict__ BsRow) {
+                                                  float *__restrict__ T1tile, int T1pitch,
+                                                  float *__restrict__ AmRow, float *__restrict__ BsRow) {
     using F = SlideGeom<K, NU, WG>;
     using G = BwdGeom<K, NU, WG>;
     constexpr int CL = F::CL, PL = F::PL, NS = F::NS, PERIOD = F::PERIOD, NT = F::NCONS;
@@ -199,7 +202,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                         for (int q = 0; q < NU; ++q) acc += stg[(g * NU + q) * 16 + xi];
                     }
                 }
-                T1tile[(int64_t)ty * G::TW + x] = acc;
+                T1tile[(int64_t)ty * T1pitch + x] = acc;
             }
         } else if (tid >= 96 && tid < 96 + 2 * F::WTC) {
             if (ty < rows) {
@@ -287,21 +290,31 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             }
             float a[4][4];
             float red[16];  // T1[0..8), Bs[0..4), Am[0..4)
+            if (has_cells) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float bs = 0.f, am = 0.f;
+                for (int i = 0; i < 4; ++i) {
+                    float bs = 0.f, am = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int di = i - j + 3;
-                    const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
-                    const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
-                    const float av = gg[i][j] * rs;                              // a  = g / den               (:135,:145)
-                    a[i][j] = av;                                                // bc = g*ey2*(exy+eps)/den^3 (:147)
-                    bs = j == 0 ? (av * e) * (ey[di] * (rs * rs)) : fmaf(av * e, ey[di] * (rs * rs), bs);
-                    am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
+                    for (int j = 0; j < 4; ++j) {
+                        const int di = i - j + 3;
+                        const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
+                        const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
+                        const float av = gg[i][j] * rs;                              // a  = g / den               (:135,:145)
+                        a[i][j] = av;                                                // bc = g*ey2*(exy+eps)/den^3 (:147)
+                        bs = j == 0 ? (av * e) * (ey[di] * (rs * rs)) : fmaf(av * e, ey[di] * (rs * rs), bs);
+                        am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
+                    }
+                    red[8 + i] = bs;
+                    red[12 + i] = am;
                 }
-                red[8 + i] = bs;
-                red[12 + i] = am;
+            } else {   // warm-up and flush steps: no cell row
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
+                    red[8 + i] = 0.f;
+                    red[12 + i] = 0.f;
+                }
             }
             // ---- vertical k-row sum of a, then the target row y = hr - r:  T1[x] += proj'[y, x - s] * sum_w va[w][s]
             float va[4][4];
@@ -365,8 +378,20 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     const int rows = min(L.RB, p.H - h0);
     // row steps: RBH to run every image row through the window ring + k-1 to flush the vertical ring of a
     const int steps = (L.RBH + K - 1 + F::PERIOD - 1) / F::PERIOD * F::PERIOD;
-    // ill-conditioned tiles belong to the direct two-pass kernels (sliding_fallback.cu)
-    if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) return;
+    // this tile's rows of the T1 image of its (band, tile) parity, and its rows of the per-chunk Am / Bs images
+    float *T1tile = (float *)(ws + BL.off_T1) +
+                    (((((int64_t)b * L.n_chunks + ch) * 2 + (nb & 1)) * 2 + (wt & 1)) * BL.Hp + h0) * BL.Wp + w_base;
+    const int64_t prow = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h0) * L.cs_pitch + w_base;
+    float *AmRow = (float *)(ws + BL.off_Am) + prow, *BsRow = (float *)(ws + BL.off_Bs) + prow;
+    // ill-conditioned tiles belong to the direct two-pass kernels (sliding_fallback.cu): contribute zeros here
+    if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) {
+        for (int e = tid; e < BL.TH * BL.TW; e += F::NCONS) T1tile[(int64_t)(e / BL.TW) * BL.Wp + e % BL.TW] = 0.f;
+        for (int e = tid; e < rows * WTC; e += F::NCONS) {
+            AmRow[(int64_t)(e / WTC) * L.cs_pitch + e % WTC] = 0.f;
+            BsRow[(int64_t)(e / WTC) * L.cs_pitch + e % WTC] = 0.f;
+        }
+        return;
+    }
 
     if (tid == 0) {
 #pragma unroll
@@ -384,22 +409,18 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     loader.init(L, ws, b, nb, h0, w_base, s_base);
     for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar);
 
-    const int64_t tile = (((int64_t)b * L.NB + nb) * L.n_wtiles + wt) * L.n_chunks + ch;
-    float *T1tile = (float *)(ws + BL.off_T1) + tile * BL.TH * BL.TW;
-    const int64_t prow = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h0) * L.cs_pitch + w_base;
-    float *AmRow = (float *)(ws + BL.off_Am) + prow, *BsRow = (float *)(ws + BL.off_Bs) + prow;
 
     // bodies as in the forward: 0 = all cells valid, 1 = 16-byte gradient loads with a validity mask, 2 = scalar
     const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
     if (vec && w_base + WTC <= p.W && w_base - (s_base + SC - 1) >= 0)
         backward_consumer<K, NU, WG, 0>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, AmRow, BsRow);
+                                        grad, T1tile, BL.Wp, AmRow, BsRow);
     else if (vec)
         backward_consumer<K, NU, WG, 1>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, AmRow, BsRow);
+                                        grad, T1tile, BL.Wp, AmRow, BsRow);
     else
         backward_consumer<K, NU, WG, 2>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, AmRow, BsRow);
+                                        grad, T1tile, BL.Wp, AmRow, BsRow);
 }
 
 // camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of
@@ -407,37 +428,45 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
 // sum_h ( sum_w q1[h,w] + cam'_h[y,x] * sum_w q2[h,w] ) with q1 = Am - Bs*A, q2 = Bs staged per 32x8 pixel block in
 // shared memory.  Fixed summation order; out-of-image cells do not exist, out-of-image targets are never computed
 // (reference :177).  Cells of flagged chunks arrive as ready-made patch gradients (sliding_fallback.cu).
-constexpr int kFinTX = 32, kFinTY = 8, kFinMaxK = 7;
+constexpr int kFinTX = 32, kFinTY = 8;
 
+// x / d for a block-local x: d-aligned base known, a short loop instead of an integer division
+__device__ __forceinline__ int div_near(int x, int d, int q0) {   // q0 * d <= x required
+    int q = q0;
+    while ((q + 1) * d <= x) ++q;
+    return q;
+}
+
+template <int K>
 __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad) {
-    __shared__ float q1[kFinTY + kFinMaxK - 1][kFinTX + kFinMaxK], q2[kFinTY + kFinMaxK - 1][kFinTX + kFinMaxK];
-    const int K = L.K, r = L.r, back = K - 1 - r;
+    constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinTY + K - 1;
+    __shared__ float q1[SH][SW + 1], q2[SH][SW + 1];
     const int x0 = blockIdx.x * kFinTX, y0 = blockIdx.y * kFinTY, b = blockIdx.z;
     const int tid = threadIdx.y * kFinTX + threadIdx.x;
     const float *T1 = (const float *)(ws + BL.off_T1);
     const float *Am = (const float *)(ws + BL.off_Am), *Bs = (const float *)(ws + BL.off_Bs);
     const float *A = (const float *)(ws + L.off_A), *camP = (const float *)(ws + L.off_camP);
     const float *patch = (const float *)(ws + BL.off_patch);
-    const uint8_t *flags = (const uint8_t *)(ws + L.off_flags), *tileany = (const uint8_t *)(ws + L.off_tileany);
-    const int SW = kFinTX + K - 1, SH = kFinTY + K - 1;
+    const uint8_t *tileany = (const uint8_t *)(ws + L.off_tileany);
+    // first band / column tile that can hold a cell of this block (block-uniform; the only divisions of the kernel)
+    const int nb_lo = max(y0 - back, 0) / L.RB, wt_lo = max(x0 - back, 0) / L.WTC;
+    const int64_t chunk_stride = (int64_t)L.NB * L.RB * L.cs_pitch;   // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
     int flagged_near = 0;
     for (int e = tid; e < SW * SH; e += kFinTX * kFinTY) {
-        const int hh = e / SW, ww = e % SW, h = y0 - back + hh, w = x0 - back + ww;
+        const int hh = e / SW, ww = e - hh * SW, h = y0 - back + hh, w = x0 - back + ww;
         float v1 = 0.f, v2 = 0.f;
         if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
-            const int64_t t3 = ((int64_t)b * L.NB + h / L.RB) * L.n_wtiles + w / L.WTC;
+            const int64_t o = ((int64_t)b * L.n_chunks * L.NB * L.RB + h) * L.cs_pitch + w;
             float am = 0.f, bs = 0.f;
-            for (int ch = 0; ch < L.n_chunks; ++ch) {
-                if (flags[t3 * L.n_chunks + ch]) continue;
-                const int64_t o = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h) * L.cs_pitch + w;
-                am += Am[o];
-                bs += Bs[o];
+            for (int ch = 0; ch < L.n_chunks; ++ch) {   // flagged tiles hold zeros
+                am += Am[o + ch * chunk_stride];
+                bs += Bs[o + ch * chunk_stride];
             }
             v1 = fmaf(-bs, A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w], am);
             v2 = bs;
-            flagged_near |= tileany[t3];
+            flagged_near |= tileany[(b * L.NB + div_near(h, L.RB, nb_lo)) * L.n_wtiles + div_near(w, L.WTC, wt_lo)];
         }
         q1[hh][ww] = v1;
         q2[hh][ww] = v2;
@@ -445,28 +474,38 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     flagged_near = __syncthreads_or(flagged_near);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= p.W || y >= p.H) return;
+    // T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does the
+    // previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts of the
+    // images are never read; flagged tiles wrote zeros.
     float acc = 0.f;
-    // T1 tiles: band nb covers target rows [nb*RB - r, nb*RB + RBH - r), tile wt covers columns [wt*WTC - r, wt*WTC + TW - r)
-    for (int nb = max(0, (y + r - L.RBH + 1) / L.RB); nb < L.NB && nb * L.RB - r <= y; ++nb) {
-        const int ty = y - (nb * L.RB - r);
-        if (ty < 0 || ty >= L.RBH) continue;
-        for (int wt = max(0, (x + r - BL.TW + 1) / L.WTC); wt < L.n_wtiles && wt * L.WTC - r <= x; ++wt) {
-            const int tx = x - (wt * L.WTC - r);
-            if (tx < 0 || tx >= BL.TW) continue;
-            for (int ch = 0; ch < L.n_chunks; ++ch) {
-                const int64_t tile = tile_index(L, b, nb, wt, ch);
-                if (!flags[tile]) acc += T1[(tile * BL.TH + ty) * BL.TW + tx];
+    {
+        const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
+        const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
+        const int64_t img = (int64_t)BL.Hp * BL.Wp;
+        const float *base = T1 + (int64_t)b * L.n_chunks * 4 * img + (int64_t)(y + r) * BL.Wp + (x + r);
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {
+            const int nb = nbA - db;
+            if (nb < 0 || nb >= L.NB || (db && ry >= K - 1)) continue;
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int wt = wtA - dw;
+                if (wt < 0 || wt >= L.n_wtiles || (dw && rx >= K - 1)) continue;
+                const float *src = base + ((nb & 1) * 2 + (wt & 1)) * img;
+                for (int ch = 0; ch < L.n_chunks; ++ch) acc += src[ch * 4 * img];
             }
         }
     }
     float sub = 0.f;
+#pragma unroll
     for (int i = 0; i < K; ++i) {
         const int h = y - i + r;
         if (h < 0 || h >= p.H) continue;
-        const int nb = h / L.RB;
+        const int nb = div_near(h, L.RB, nb_lo);
         const float cv = camP[(((int64_t)b * L.NB + nb) * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
         const int hh = threadIdx.y + K - 1 - i;
         float s1 = 0.f, s2 = 0.f;
+#pragma unroll
         for (int j = 0; j < K; ++j) {
             s1 += q1[hh][threadIdx.x + K - 1 - j];
             s2 += q2[hh][threadIdx.x + K - 1 - j];
@@ -476,7 +515,7 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             for (int j = 0; j < K; ++j) {
                 const int w = x - j + r;
                 if (w < 0 || w >= p.W) continue;
-                if (tileany[((int64_t)b * L.NB + nb) * L.n_wtiles + w / L.WTC])
+                if (tileany[((int64_t)b * L.NB + nb) * L.n_wtiles + div_near(w, L.WTC, wt_lo)])
                     sub -= patch[(((int64_t)b * p.H + h) * p.W + w) * (K * K) + i * K + j];
             }
         }
@@ -531,8 +570,8 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     }
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;
-    sliding_backward_finalize_kernel<<<dim3((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B),
-                                       dim3(kFinTX, kFinTY), 0, stream>>>(p, L, BL, ws, camera_grad);
+    sliding_backward_finalize_kernel<5><<<dim3((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B),
+                                          dim3(kFinTX, kFinTY), 0, stream>>>(p, L, BL, ws, camera_grad);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;
 }

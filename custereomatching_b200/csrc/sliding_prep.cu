@@ -124,10 +124,17 @@ __global__ void __launch_bounds__(256)
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
     }
-    if ((threadIdx.x & 31) == 0 && vmax >= vmin) {
-        uint32_t *mm = minmax + ((size_t)(img * p.B + b) * L.NB + nb) * 2;
-        atomicMax(mm, float_to_ordered(vmax));
-        atomicMax(mm + 1, float_to_ordered(-vmin));
+    __shared__ float smax[8], smin[8];
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = vmax; smin[threadIdx.x >> 5] = vmin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int wi = 1; wi < 8; ++wi) { vmax = fmaxf(vmax, smax[wi]); vmin = fminf(vmin, smin[wi]); }
+        if (vmax >= vmin) {   // one pair of atomics per block
+            uint32_t *mm = minmax + ((size_t)(img * p.B + b) * L.NB + nb) * 2;
+            atomicMax(mm, float_to_ordered(vmax));
+            atomicMax(mm + 1, float_to_ordered(-vmin));
+        }
     }
 }
 
@@ -272,7 +279,7 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
     CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_end, 0x7f, L.big_end - L.zero_end, stream));
     {
         const int64_t n = (int64_t)L.RBH * p.W;
-        dim3 grid((unsigned)std::min<int64_t>((n + 1023) / 1024, 64), L.NB, 2 * p.B);
+        dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, 2 * p.B);
         band_minmax_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax);
         CUSTMA_LAUNCH_CHECK("band_minmax_kernel");
     }
