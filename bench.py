@@ -149,8 +149,7 @@ def cpu_torch_port_rate(H, W, D, k, budget_s=12.0, max_rows=None, threads=None):
     a band of image rows of ONE pair of the workload's shape.  Returns (Mcells/s, description, threads)."""
     import torch
     from oracle import zncc_oracle as zo
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
     rows = min(H, max_rows or H)
     gen = torch.Generator().manual_seed(0)
     cam = torch.rand(rows, W, generator=gen)
@@ -180,6 +179,7 @@ def run_reference_cpu(args):
     H, W, D, k, _, desc = WORKLOADS[args.workload]
     import torch
     from oracle import zncc_oracle as zo
+    torch.set_num_threads(os.cpu_count() or 1)               # all host threads; torchrun exports OMP_NUM_THREADS=1
     rows = min(H, args.ref_rows)
     gen = torch.Generator().manual_seed(0)
     cam = torch.rand(rows, W, generator=gen)
@@ -272,6 +272,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")               # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     H, W, D, k, default_pairs, desc = WORKLOADS[args.workload]

@@ -23,6 +23,8 @@ namespace custma {
 
 constexpr int kGradStages = 4;     // ring of upstream-gradient rows in shared memory
 constexpr int kGradLookahead = 3;  // steps between issuing a gradient row and using it
+constexpr int kBwdLookahead = 4;   // row slots are refilled 4 steps ahead, from the slot every warp released 4 steps ago
+                                   // (8 slots): warps may drift up to 4 steps apart before anyone waits
 
 template <int K, int NU, int WG>
 struct BwdGeom {
@@ -225,12 +227,13 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
         for (int q = 0; q < PERIOD; ++q) {
             const int t = t0 + q;
             const int slot = t & (NS - 1);
-            // ---- refill the slot of step t + lookahead (used last by step t - 2), after finishing that step's sums
-            if (t >= 2) {
-                mbar_wait(&empty_bar[(t - 2) & (NS - 1)], ((t - 2) / NS) & 1);
-                reduce_step(t - 2);
+            // ---- refill the slot of step t + lookahead (used last by step t + lookahead - 8), after finishing that step's sums
+            if (t >= NS - kBwdLookahead) {
+                const int ts = t - (NS - kBwdLookahead);
+                mbar_wait(&empty_bar[ts & (NS - 1)], (ts / NS) & 1);
+                reduce_step(ts);
             }
-            if (t + kLookahead < steps) loader.issue(t + kLookahead, smem, full_bar);
+            if (t + kBwdLookahead < steps) loader.issue(t + kBwdLookahead, smem, full_bar);
             // ---- prefetch the upstream gradient row that step t + kGradLookahead consumes
             if (MODE != 2) {
                 const int hp = t + kGradLookahead - (K - 1);
@@ -346,17 +349,19 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                     *reinterpret_cast<float4 *>(xps + l16 * G::XPOSE_STRIDE + 4 * v) =
                         make_float4(red[4 * v], red[4 * v + 1], red[4 * v + 2], red[4 * v + 3]);
                 __syncwarp();
-                float tot = xps[l16];
+                float part[4];   // fixed tree: four chains of four instead of one chain of sixteen
 #pragma unroll
-                for (int m = 1; m < 16; ++m) tot += xps[m * G::XPOSE_STRIDE + l16];
-                S[G::OFF_STG + u * 16 + l16] = tot;
+                for (int m = 0; m < 4; ++m)
+                    part[m] = (xps[(4 * m) * G::XPOSE_STRIDE + l16] + xps[(4 * m + 1) * G::XPOSE_STRIDE + l16]) +
+                              (xps[(4 * m + 2) * G::XPOSE_STRIDE + l16] + xps[(4 * m + 3) * G::XPOSE_STRIDE + l16]);
+                S[G::OFF_STG + u * 16 + l16] = (part[0] + part[1]) + (part[2] + part[3]);
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
         }
     }
-    // the sums of the last two steps
-    for (int ts = steps - 2; ts < steps; ++ts) {
+    // the sums of the last steps
+    for (int ts = steps - (NS - kBwdLookahead); ts < steps; ++ts) {
         if (ts < 0) continue;
         mbar_wait(&empty_bar[ts & (NS - 1)], (ts / NS) & 1);
         reduce_step(ts);
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     __syncthreads();
     BwdRowLoader<K, NU, WG> loader;
     loader.init(L, ws, b, nb, h0, w_base, s_base);
-    for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar);
+    for (int t = 0; t < kBwdLookahead && t < steps; ++t) loader.issue(t, smem, full_bar);
 
 
     // bodies as in the forward: 0 = all cells valid, 1 = 16-byte gradient loads with a validity mask, 2 = scalar
@@ -454,22 +459,34 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     const int nb_lo = max(y0 - back, 0) / L.RB, wt_lo = max(x0 - back, 0) / L.WTC;
     const int64_t chunk_stride = (int64_t)L.NB * L.RB * L.cs_pitch;   // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
     int flagged_near = 0;
-    for (int e = tid; e < SW * SH; e += kFinTX * kFinTY) {
-        const int hh = e / SW, ww = e - hh * SW, h = y0 - back + hh, w = x0 - back + ww;
-        float v1 = 0.f, v2 = 0.f;
-        if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
-            const int64_t o = ((int64_t)b * L.n_chunks * L.NB * L.RB + h) * L.cs_pitch + w;
-            float am = 0.f, bs = 0.f;
-            for (int ch = 0; ch < L.n_chunks; ++ch) {   // flagged tiles hold zeros
-                am += Am[o + ch * chunk_stride];
-                bs += Bs[o + ch * chunk_stride];
+    static_assert(SH <= 2 * kFinTY && SW <= 2 * kFinTX, "two passes of the thread block cover the staged cells");
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        const int hh = threadIdx.y + ph * kFinTY, h = y0 - back + hh;
+        if (hh >= SH) continue;
+        const bool h_ok = h >= 0 && h < p.H;
+        const int nb = h_ok ? div_near(h, L.RB, nb_lo) : 0;
+        const float *am_row = Am + ((int64_t)b * L.n_chunks * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
+        const float *bs_row = Bs + ((int64_t)b * L.n_chunks * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
+        const float *a_row = A + ((int64_t)b * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+            const int ww = threadIdx.x + pw * kFinTX, w = x0 - back + ww;
+            if (ww >= SW) continue;
+            float v1 = 0.f, v2 = 0.f;
+            if (h_ok && w >= 0 && w < p.W) {
+                float am = 0.f, bs = 0.f;
+                for (int ch = 0; ch < L.n_chunks; ++ch) {   // flagged tiles hold zeros
+                    am += am_row[w + ch * chunk_stride];
+                    bs += bs_row[w + ch * chunk_stride];
+                }
+                v1 = fmaf(-bs, a_row[w], am);
+                v2 = bs;
+                flagged_near |= tileany[(b * L.NB + nb) * L.n_wtiles + div_near(w, L.WTC, wt_lo)];
             }
-            v1 = fmaf(-bs, A[((int64_t)b * L.NB * L.RB + h) * L.cs_pitch + w], am);
-            v2 = bs;
-            flagged_near |= tileany[(b * L.NB + div_near(h, L.RB, nb_lo)) * L.n_wtiles + div_near(w, L.WTC, wt_lo)];
+            q1[hh][ww] = v1;
+            q2[hh][ww] = v2;
         }
-        q1[hh][ww] = v1;
-        q2[hh][ww] = v2;
     }
     flagged_near = __syncthreads_or(flagged_near);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
