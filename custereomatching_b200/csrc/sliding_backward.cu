@@ -447,28 +447,33 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad) {
     constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinTY + K - 1;
+    static_assert(SH <= 2 * kFinTY && SW <= 2 * kFinTX, "two passes of the thread block cover the staged cells");
     __shared__ float q1[SH][SW + 1], q2[SH][SW + 1];
     const int x0 = blockIdx.x * kFinTX, y0 = blockIdx.y * kFinTY, b = blockIdx.z;
-    const int tid = threadIdx.y * kFinTX + threadIdx.x;
-    const float *T1 = (const float *)(ws + BL.off_T1);
-    const float *Am = (const float *)(ws + BL.off_Am), *Bs = (const float *)(ws + BL.off_Bs);
-    const float *A = (const float *)(ws + L.off_A), *camP = (const float *)(ws + L.off_camP);
-    const float *patch = (const float *)(ws + BL.off_patch);
-    const uint8_t *tileany = (const uint8_t *)(ws + L.off_tileany);
-    // first band / column tile that can hold a cell of this block (block-uniform; the only divisions of the kernel)
+    // block-uniform bases (64-bit once); per-thread offsets stay 32-bit (every image of one pair is < 2^31 floats)
+    const int chunk_stride = L.NB * L.RB * L.cs_pitch;                      // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
+    const float *Am = (const float *)(ws + BL.off_Am) + (int64_t)b * L.n_chunks * chunk_stride;
+    const float *Bs = (const float *)(ws + BL.off_Bs) + (int64_t)b * L.n_chunks * chunk_stride;
+    const float *A = (const float *)(ws + L.off_A) + (int64_t)b * chunk_stride;
+    const float *camP = (const float *)(ws + L.off_camP) + (int64_t)b * L.NB * L.RBH * L.cam_pitch;
+    const int img = BL.Hp * BL.Wp;                                          // T1: [B][n_chunks][2][2][Hp][Wp]
+    const float *T1 = (const float *)(ws + BL.off_T1) + (int64_t)b * L.n_chunks * 4 * img;
+    const uint8_t *tileany = (const uint8_t *)(ws + L.off_tileany) + (int64_t)b * L.NB * L.n_wtiles;
+    // first band / column tile that can hold a cell of this block (the only divisions of the kernel)
     const int nb_lo = max(y0 - back, 0) / L.RB, wt_lo = max(x0 - back, 0) / L.WTC;
-    const int64_t chunk_stride = (int64_t)L.NB * L.RB * L.cs_pitch;   // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
     int flagged_near = 0;
-    static_assert(SH <= 2 * kFinTY && SW <= 2 * kFinTX, "two passes of the thread block cover the staged cells");
+    {
+        const int nb_hi = min((y0 + kFinTY - 1 + r) / L.RB, L.NB - 1), wt_hi = min((x0 + kFinTX - 1 + r) / L.WTC, L.n_wtiles - 1);
+        for (int nb = nb_lo; nb <= nb_hi; ++nb)
+            for (int wt = wt_lo; wt <= wt_hi; ++wt) flagged_near |= tileany[nb * L.n_wtiles + wt];
+    }
+    // ---- stage q1 = Am - Bs * A and q2 = Bs (summed over the chunks; flagged tiles hold zeros) for the cells around
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph) {
         const int hh = threadIdx.y + ph * kFinTY, h = y0 - back + hh;
         if (hh >= SH) continue;
         const bool h_ok = h >= 0 && h < p.H;
-        const int nb = h_ok ? div_near(h, L.RB, nb_lo) : 0;
-        const float *am_row = Am + ((int64_t)b * L.n_chunks * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
-        const float *bs_row = Bs + ((int64_t)b * L.n_chunks * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
-        const float *a_row = A + ((int64_t)b * L.NB * L.RB + (h_ok ? h : 0)) * L.cs_pitch;
+        const int row = (h_ok ? h : 0) * L.cs_pitch;
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw) {
             const int ww = threadIdx.x + pw * kFinTX, w = x0 - back + ww;
@@ -476,30 +481,28 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             float v1 = 0.f, v2 = 0.f;
             if (h_ok && w >= 0 && w < p.W) {
                 float am = 0.f, bs = 0.f;
-                for (int ch = 0; ch < L.n_chunks; ++ch) {   // flagged tiles hold zeros
-                    am += am_row[w + ch * chunk_stride];
-                    bs += bs_row[w + ch * chunk_stride];
+                for (int ch = 0; ch < L.n_chunks; ++ch) {
+                    am += Am[row + w + ch * chunk_stride];
+                    bs += Bs[row + w + ch * chunk_stride];
                 }
-                v1 = fmaf(-bs, a_row[w], am);
+                v1 = fmaf(-bs, A[row + w], am);
                 v2 = bs;
-                flagged_near |= tileany[(b * L.NB + nb) * L.n_wtiles + div_near(w, L.WTC, wt_lo)];
             }
             q1[hh][ww] = v1;
             q2[hh][ww] = v2;
         }
     }
-    flagged_near = __syncthreads_or(flagged_near);
+    __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= p.W || y >= p.H) return;
-    // T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does the
-    // previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts of the
-    // images are never read; flagged tiles wrote zeros.
+    // ---- T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does
+    // the previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts of
+    // the images are never read.
+    const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
+    const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
     float acc = 0.f;
     {
-        const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
-        const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
-        const int64_t img = (int64_t)BL.Hp * BL.Wp;
-        const float *base = T1 + (int64_t)b * L.n_chunks * 4 * img + (int64_t)(y + r) * BL.Wp + (x + r);
+        const int off = (y + r) * BL.Wp + (x + r);
 #pragma unroll
         for (int db = 0; db < 2; ++db) {
             const int nb = nbA - db;
@@ -508,18 +511,19 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             for (int dw = 0; dw < 2; ++dw) {
                 const int wt = wtA - dw;
                 if (wt < 0 || wt >= L.n_wtiles || (dw && rx >= K - 1)) continue;
-                const float *src = base + ((nb & 1) * 2 + (wt & 1)) * img;
+                const float *src = T1 + ((nb & 1) * 2 + (wt & 1)) * img + off;
                 for (int ch = 0; ch < L.n_chunks; ++ch) acc += src[ch * 4 * img];
             }
         }
     }
+    // ---- per-pixel terms: cell rows h = y + r - i, i < k; row h = y + r - i is in band nbA unless i > ry
     float sub = 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const int h = y - i + r;
         if (h < 0 || h >= p.H) continue;
-        const int nb = div_near(h, L.RB, nb_lo);
-        const float cv = camP[(((int64_t)b * L.NB + nb) * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
+        const int nb = i <= ry ? nbA : nbA - 1;
+        const float cv = camP[(nb * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
         const int hh = threadIdx.y + K - 1 - i;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -528,16 +532,23 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             s2 += q2[hh][threadIdx.x + K - 1 - j];
         }
         sub += fmaf(cv, s2, s1);
-        if (flagged_near) {
+    }
+    acc -= sub;
+    if (flagged_near) {   // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178 as a gather)
+        const float *patch = (const float *)(ws + BL.off_patch) + (int64_t)b * p.H * p.W * (K * K);
+        for (int i = 0; i < K; ++i) {
+            const int h = y - i + r;
+            if (h < 0 || h >= p.H) continue;
+            const int nb = i <= ry ? nbA : nbA - 1;
             for (int j = 0; j < K; ++j) {
                 const int w = x - j + r;
                 if (w < 0 || w >= p.W) continue;
-                if (tileany[((int64_t)b * L.NB + nb) * L.n_wtiles + div_near(w, L.WTC, wt_lo)])
-                    sub -= patch[(((int64_t)b * p.H + h) * p.W + w) * (K * K) + i * K + j];
+                if (tileany[nb * L.n_wtiles + (j <= rx ? wtA : wtA - 1)])
+                    acc += patch[((int64_t)h * p.W + w) * (K * K) + i * K + j];
             }
         }
     }
-    camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc - sub;
+    camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc;
 }
 
 template <int K, int NU, int WG>
