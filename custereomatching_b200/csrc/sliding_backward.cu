@@ -594,6 +594,7 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     switch (cfg.NU) {
         case 1: rc = launch_bwd_cfg<5, 1, 16>(p, L, BL, ws, grad, stream); break;
         case 2: rc = launch_bwd_cfg<5, 2, 8>(p, L, BL, ws, grad, stream); break;
+        case 3: rc = launch_bwd_cfg<5, 3, 5>(p, L, BL, ws, grad, stream); break;
         default: rc = launch_bwd_cfg<5, 4, 4>(p, L, BL, ws, grad, stream); break;
     }
     if (rc) return rc;

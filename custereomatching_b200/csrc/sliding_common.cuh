@@ -148,9 +148,10 @@ struct SlideGeom {
                          SEG_PS = 4 * (WG + 16 * NU - 2) + 8;
     static constexpr int OFF_PROJ = SEG_CAM, OFF_A = OFF_PROJ + SEG_PROJ, OFF_EX2 = OFF_A + SEG_CS,
                          OFF_SP = OFF_EX2 + SEG_CS, OFF_EY2 = OFF_SP + SEG_PS, SLOT = OFF_EY2 + SEG_PS;
-    static constexpr int NCONS = 16 * NU * WG, NCW = NCONS / 32, NS = kSlidingStages;
+    static constexpr int NCONS = 16 * NU * WG, NCW = (NCONS + 31) / 32, NS = kSlidingStages;
     static constexpr int PERIOD = K - 2;  // length of the pair-sum ring == unroll factor of the row loop
-    static_assert(NCONS % 32 == 0, "consumer threads must fill whole warps");
+    // NCONS need not be a multiple of 32: the backward (no warp shuffles) runs 15 units = 240 threads for 192
+    // disparities; the forward's WTA reduction shuffles within half-warps and uses whole warps only
     static_assert(K % 2 == 1 && K >= 3, "pair-sum ring is written for odd k");
 };
 

@@ -27,10 +27,9 @@ bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg) {
         cfg->WG = wg[cfg->NU];
     } else {
         // backward: two register rings per cell (window sum + vertical sum of a) need ~250 registers: one CTA of
-        // 256 threads per SM, so NU * WG = 16; 129..192 disparities run as chunks of 64 rather than wasting a
-        // quarter of a 256-wide chunk
-        if (cfg->NU == 3) cfg->NU = 1;
-        cfg->WG = 16 / cfg->NU;
+        // at most 256 threads per SM, so NU * WG <= 16
+        const int wg[5] = {0, 16, 8, 5, 4};   // NU = 3: 15 units = 240 threads (the last warp is half full)
+        cfg->WG = wg[cfg->NU];
     }
     return true;
 }
