@@ -160,6 +160,8 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     using F = SlideGeom<K, NU, WG>;
     using G = BwdGeom<K, NU, WG>;
     constexpr int CL = F::CL, PL = F::PL, NS = F::NS, PERIOD = F::PERIOD, NT = F::NCONS;
+    // gradient row hr is consumed at step hr + K - 1, so it cannot be requested more than K - 1 steps ahead
+    constexpr int GLA = kGradLookahead < K - 1 ? kGradLookahead : K - 1;
     const int tid = threadIdx.x;
     const int l16 = tid & 15, u = tid >> 4, su = u % NU, wg = u / NU;
     const int w0 = w_base + 4 * wg, s0 = s_base + 64 * su + 4 * l16;
@@ -234,9 +236,9 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                 reduce_step(ts);
             }
             if (t + kBwdLookahead < steps) loader.issue(t + kBwdLookahead, smem, full_bar);
-            // ---- prefetch the upstream gradient row that step t + kGradLookahead consumes
+            // ---- prefetch the upstream gradient row that step t + GLA consumes
             if (MODE != 2) {
-                const int hp = t + kGradLookahead - (K - 1);
+                const int hp = t + GLA - (K - 1);
                 if (hp >= 0 && hp < rows) {
                     float *gdst = gsm + ((hp & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
 #pragma unroll
@@ -269,7 +271,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
             *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
             if (MODE != 2) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(kGradLookahead) : "memory");
+                asm volatile("cp.async.wait_group %0;" ::"n"(GLA) : "memory");
                 const float *gs = has_cells ? gsm + ((hr & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid : gzero;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -563,6 +565,17 @@ static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLay
     return CUSTMA_OK;
 }
 
+template <int K>
+static int launch_bwd_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws,
+                        const float *grad, cudaStream_t stream) {
+    switch (cfg.NU) {
+        case 1: return launch_bwd_cfg<K, 1, 16>(p, L, BL, ws, grad, stream);
+        case 2: return launch_bwd_cfg<K, 2, 8>(p, L, BL, ws, grad, stream);
+        case 3: return launch_bwd_cfg<K, 3, 5>(p, L, BL, ws, grad, stream);
+        default: return launch_bwd_cfg<K, 4, 4>(p, L, BL, ws, grad, stream);
+    }
+}
+
 bool sliding_backward_supported(const Problem &p) {
     SlidingConfig cfg;
     return sliding_pick_config(p, true, &cfg);
@@ -591,16 +604,12 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     char *ws = (char *)workspace;
     int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
     if (rc) return rc;
-    switch (cfg.NU) {
-        case 1: rc = launch_bwd_cfg<5, 1, 16>(p, L, BL, ws, grad, stream); break;
-        case 2: rc = launch_bwd_cfg<5, 2, 8>(p, L, BL, ws, grad, stream); break;
-        case 3: rc = launch_bwd_cfg<5, 3, 5>(p, L, BL, ws, grad, stream); break;
-        default: rc = launch_bwd_cfg<5, 4, 4>(p, L, BL, ws, grad, stream); break;
-    }
+    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, stream) : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, stream);
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;
-    sliding_backward_finalize_kernel<5><<<dim3((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B),
-                                          dim3(kFinTX, kFinTY), 0, stream>>>(p, L, BL, ws, camera_grad);
+    const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B), fblock(kFinTX, kFinTY);
+    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad);
+    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;
 }

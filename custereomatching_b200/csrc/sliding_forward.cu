@@ -274,7 +274,9 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
     int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
     if (rc) return rc;
     unsigned long long *keys = best ? (unsigned long long *)(ws + L.off_wta) : nullptr;
-    rc = launch_k<5>(cfg, p, L, ws, cost, keys, stream);
+    rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, stream)
+       : p.k == 5 ? launch_k<5>(cfg, p, L, ws, cost, keys, stream)
+                  : launch_k<7>(cfg, p, L, ws, cost, keys, stream);
     if (rc) return rc;
     if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, stream))) return rc;
     if (best) {

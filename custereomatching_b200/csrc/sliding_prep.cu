@@ -17,7 +17,8 @@
 namespace custma {
 
 bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg) {
-    if (p.k != 5) return false;
+    // instances: forward k = 3, 5, 7; backward k = 3, 5 (its per-thread partial-sum layout holds k + 3 <= 8 columns)
+    if (!(p.k == 3 || p.k == 5 || (p.k == 7 && !backward))) return false;
     cfg->K = p.k;
     const int span = p.banded ? p.D : p.W + 32;
     cfg->NU = span <= 64 ? 1 : span <= 128 ? 2 : span <= 192 ? 3 : 4;

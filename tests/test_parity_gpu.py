@@ -88,6 +88,8 @@ def test_cfg1_reference_fixture(flags):
 BANDED_CASES = [  # H, W, D, k
     (24, 40, 16, 5), (17, 33, 7, 3), (9, 21, 32, 5), (12, 50, 64, 7), (30, 47, 1, 5), (16, 64, 64, 4),
     (5, 96, 48, 15), (3, 10, 4, 5), (40, 131, 96, 5), (2, 2, 2, 1), (33, 260, 192, 5), (64, 300, 256, 5),
+    # fast-path instances for the other window sizes, with interior / masked / scalar tiles and several row bands
+    (150, 300, 64, 3), (70, 420, 192, 3), (90, 300, 64, 7), (40, 280, 128, 7), (200, 520, 192, 5), (37, 700, 100, 5),
 ]
 
 
