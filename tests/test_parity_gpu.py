@@ -322,3 +322,75 @@ def test_cfg3_middlebury_full_size_properties():
     gref = ref_port.backward_banded(gsub, cam[lo:hi], proj[lo:hi], k)
     assert_grad_close(gc[lo:hi], gref)
     assert np.abs(gc[:lo]).max() == 0 and np.abs(gc[hi:]).max() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# partitioning on the GPU: the per-rank work of the two shardings, executed rank by rank on one device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_band_ranks_reproduce_the_single_gpu_result(world):
+    """Each emulated rank computes volume rows [h0,h1) from its haloed crop (custereomatching_b200/sharding.py);
+    bands stitched together equal the unsharded result (costs / WTA bit-exact, gradient to rounding)."""
+    from custereomatching_b200 import sharding as sh
+    H, W, D, k = 83, 300, 64, 5
+    cam, proj = rand_pair(H, W, 51)
+    camd, projd = dev(cam), dev(proj)
+    gfull = dev(np.random.RandomState(6).randn(H, W, D).astype(np.float32))
+    cost, best, disp = cb.forward(camd, projd, D, k, want_cost=True, want_wta=True)
+    grad = cb.backward(gfull, camd, projd, k, D)
+    grad_sum = torch.zeros_like(grad)
+    for rank in range(world):
+        band = sh.row_band(H, k, rank, world)
+        cam_c, proj_c = sh.crop_rows_with_halo(camd, band), sh.crop_rows_with_halo(projd, band)
+        c, b, d = cb.forward(cam_c, proj_c, D, k, want_cost=True, want_wta=True)
+        assert_cost_close(sh.band_rows_of(c, band).cpu().numpy(), cost[band.h0:band.h1].cpu().numpy(), 2e-6)
+        sel = (torch.topk(cost[band.h0:band.h1], 2, dim=-1).values.diff(dim=-1).abs() > COST_TOL)[..., 0]
+        assert torch.equal(sh.band_rows_of(d, band)[sel], disp[band.h0:band.h1][sel])
+        g_crop = torch.zeros_like(c)
+        b0, b1 = sh.band_gradient_mask_rows(band)
+        g_crop[b0:b1] = gfull[band.h0:band.h1]
+        grad_sum[band.lo:band.hi] += cb.backward(g_crop, cam_c, proj_c, k, D)
+    assert_grad_close(grad_sum.cpu().numpy(), grad.cpu().numpy())
+
+
+def test_batch_slices_reproduce_the_batched_result():
+    from custereomatching_b200 import sharding as sh
+    B, H, W, D, k = 5, 40, 200, 64, 5
+    cam, proj = rand_pair(H, W, 61, B=B)
+    g = dev(np.random.RandomState(8).randn(B, H, W, D).astype(np.float32))
+    cost, best, disp = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True)
+    grad = cb.backward(g, dev(cam), dev(proj), k, D)
+    for rank in range(2):
+        b0, b1 = sh.batch_slice(B, rank, 2)
+        c, b, d = cb.forward(dev(cam[b0:b1]), dev(proj[b0:b1]), D, k, want_cost=True, want_wta=True)
+        assert torch.equal(c, cost[b0:b1]) and torch.equal(b, best[b0:b1]) and torch.equal(d, disp[b0:b1])
+        assert torch.equal(cb.backward(g[b0:b1].contiguous(), dev(cam[b0:b1]), dev(proj[b0:b1]), k, D), grad[b0:b1])
+
+
+def test_more_than_2_31_cells():
+    """One row band of BASELINE.json configs[4] (7680 wide, 512 disparities): 2.4e9 cells - past the int32 element
+    count the reference overflows at (custma/src/stereo_matching_kernel.cu:194).  Size-independent checks."""
+    H, W, D, k = 600, 7680, 512, 5
+    assert H * W * D > 2 ** 31
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    cam = torch.rand(H, W, device="cuda", generator=gen)
+    proj = torch.rand(H, W, device="cuda", generator=gen)
+    cost, best, disp = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True)
+    for rows in [(0, 3), (297, 300), (597, 600)]:       # first, middle and last rows (the last ones live past 2^31)
+        _row_crop_check(cam.cpu().numpy(), proj.cpu().numpy(), cost, None, D, k, rows, H)
+        h0, h1 = rows
+        tb, ti = torch.flip(cost[h0:h1], dims=[-1]).max(dim=-1)
+        assert torch.equal(best[h0:h1], tb) and torch.equal(disp[h0:h1].long(), (D - 1) - ti)
+    # backward of a gradient that lives only in the last rows, against the oracle on the cropped rows
+    g = torch.zeros_like(cost)
+    del cost
+    h0, h1 = 596, 600
+    g[h0:h1] = torch.randn(h1 - h0, W, D, device="cuda", generator=gen)
+    gc = cb.backward(g, cam, proj, k, D).cpu().numpy()
+    r = k // 2
+    lo = h0 - r
+    gsub = np.zeros((H - lo, W, D), np.float32)
+    gsub[h0 - lo:] = g[h0:h1].cpu().numpy()
+    gref = ref_port.backward_banded(gsub, cam[lo:].cpu().numpy(), proj[lo:].cpu().numpy(), k)
+    assert_grad_close(gc[lo:], gref)
+    assert np.abs(gc[:lo]).max() == 0
