@@ -7,9 +7,10 @@
 //                        what makes the O(1)-per-cell window sums safe in fp32.
 //   band_copy_kernel     pivoted copies with aprons: out-of-image pixels hold (0 - pivot), i.e. the reference's zero
 //                        padding (query_ij, kernel.cu:6-12) in pivoted coordinates.
-//   band_stats_kernel    per pixel: window sum and centred second moment of the PIVOTED values, two passes in the
-//                        reference's order (kernel.cu:40-70).  Statistics are taken from the shifted data so that
+//   band_stats_kernel    per pixel: window sum and centred second moment (one pass, sum v^2 - (sum v)^2 / n) of the
+//                        PIVOTED values.  Statistics are taken from the shifted data so that
 //                        exy = sum(cam'*proj') - A*Sp cancels consistently.
+//   tile_flags_kernel    per tile: can the fp32 error of the raw window sums exceed the tolerance?  (-> fallback)
 #include <algorithm>
 
 #include "sliding_common.cuh"
@@ -182,12 +183,17 @@ __global__ void __launch_bounds__(256)
 // horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  One-pass second moment
 // e2 = sum v^2 - (sum v)^2 / n on band-pivoted data: its error, eps * n * max|v|^2, is what the tile verdict bounds.
 // camera: A = window mean, ex2;   projector: Sp = window sum, ey2;   plus min e2 per block of 16 columns.
+constexpr int kStatRows = 16;   // output rows per thread of band_stats_kernel
+
 template <int K>
 __global__ void __launch_bounds__(128)
     band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ camP, const float *__restrict__ projP,
                       float *__restrict__ A, float *__restrict__ ex2, float *__restrict__ Sp,
                       float *__restrict__ ey2, float *__restrict__ e2min_c, float *__restrict__ e2min_p) {
-    const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y;
+    // blockIdx.y = band * segments + segment: a thread marches kStatRows output rows (+ k-1 warm-up rows) of one column
+    const int nseg = (L.RB + kStatRows - 1) / kStatRows;
+    const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y / nseg, seg = blockIdx.y % nseg;
+    const int t_begin = seg * kStatRows, t_end = min(L.RBH, t_begin + kStatRows + K - 1);
     const int pitch = img ? L.ps_pitch : L.cs_pitch, left = img ? L.ps_ld : 0;
     const int pitchP = img ? L.proj_pitch : L.cam_pitch, leftP = img ? L.proj_lp : L.cam_lc;
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
     for (int m = 0; m < K - 1; ++m) r1[m] = r2[m] = 0.f;
     float emin = 3.0e38f;
-    for (int t = 0; t < L.RBH; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
         float h1 = 0.f, h2 = 0.f;
         if (col_ok) {
 #pragma unroll
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(128)
         for (int m = 0; m < K - 2; ++m) { r1[m] = r1[m + 1]; r2[m] = r2[m + 1]; }
         r1[K - 2] = h1; r2[K - 2] = h2;
         const int hr = t - (K - 1);
-        if (hr >= 0 && ci < pitch) {
+        if (hr >= t_begin && ci < pitch) {
             const bool ok = col_ok && nb * L.RB + hr < p.H;
             const float mean = s1 * inv_n;
             const float e2 = fmaxf(fmaf(-s1, mean, s2), 0.f);
@@ -289,7 +295,7 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
-        dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB, 2 * p.B);
+        dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB * ((L.RB + kStatRows - 1) / kStatRows), 2 * p.B);
         auto kern = p.k == 3 ? band_stats_kernel<3> : p.k == 5 ? band_stats_kernel<5> : band_stats_kernel<7>;
         kern<<<grid, 128, 0, stream>>>(p, L, camP, projP, (float *)(ws + L.off_A), (float *)(ws + L.off_ex2),
                                        (float *)(ws + L.off_Sp), (float *)(ws + L.off_ey2), e2min_c, e2min_p);
