@@ -28,6 +28,7 @@ SYMBOLS = (
     "custma_abi_version",
     "custma_last_error",
     "custma_launch_count",
+    "custma_debug_validate_layout",
     "custma_forward_workspace_bytes",
     "custma_backward_workspace_bytes",
     "custma_forward",
@@ -56,6 +57,8 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = _size
         fn.argtypes = [_i32, _i32, _i32, _i32, _i32, _u32]
+    lib.custma_debug_validate_layout.restype = ctypes.c_int
+    lib.custma_debug_validate_layout.argtypes = [_i32, _i32, _i32, _i32, _i32]
     lib.custma_forward.restype = ctypes.c_int
     lib.custma_forward.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward.restype = ctypes.c_int
@@ -98,6 +101,10 @@ def launch_count() -> int:
 def check(rc: int, what: str) -> None:
     if rc != OK:
         raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def validate_layout(B, H, W, D, k) -> None:
+    check(load().custma_debug_validate_layout(B, H, W, D, k), "custma_debug_validate_layout")
 
 
 def forward_workspace_bytes(B, H, W, D, k, flags=0) -> int:

@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "sliding_common.cuh"
 
 namespace custma {
 
@@ -99,6 +99,14 @@ size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t 
     Problem p;
     if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
     return backward_ws(p, flags);
+}
+
+int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if ((rc = validate_sliding_layout(p, false))) return rc;
+    return validate_sliding_layout(p, true);
 }
 
 int custma_forward(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,

@@ -256,6 +256,7 @@ struct RowLoader {
 // host side (sliding_prep.cu)
 bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg);
 void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backward, SlidingLayout *L);
+int validate_sliding_layout(const Problem &p, bool backward);
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
                         cudaStream_t stream);
 // sliding_fallback.cu: the flagged tiles, cell by cell in the reference's arithmetic

@@ -106,6 +106,51 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->total = off;
 }
 
+// Host-side self-check of the tiling: every segment a kernel copies out of the workspace arrays must lie inside its
+// row and be 16-byte aligned, for every tile of the problem.  (compute-sanitizer is not available on the test pool;
+// tests/test_layout_cpu.py sweeps shapes through this instead.)
+int validate_sliding_layout(const Problem &p, bool backward) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, backward, &cfg)) return CUSTMA_OK;   // no fast-path instance: nothing to check
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, backward, &L);
+    auto bad = [&](const char *what, int wt, int c, int a, int b) {
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "layout check failed: %s (tile %d chunk %d: %d vs %d) for B=%d H=%d W=%d D=%d k=%d %s",
+                         what, wt, c, a, b, p.B, p.H, p.W, p.D, p.k, backward ? "backward" : "forward");
+    };
+    if (L.RB < 1 || (L.RB + L.K - 1) % (L.K - 2) != 0) return bad("band height", 0, 0, L.RB, L.K);
+    if (L.NB * L.RB < p.H || (L.NB - 1) * L.RB >= p.H) return bad("band count", 0, 0, L.NB * L.RB, p.H);
+    if ((L.cam_pitch | L.proj_pitch | L.cs_pitch | L.ps_pitch) & 3) return bad("pitch alignment", 0, 0, L.cam_pitch, L.proj_pitch);
+    if (L.n_wtiles * L.WTC < p.W) return bad("column tiles", 0, 0, L.n_wtiles * L.WTC, p.W);
+    for (int wt = 0; wt < L.n_wtiles; ++wt) {
+        const int w_base = wt * L.WTC;
+        const int c0 = w_base - L.r + L.cam_lc;
+        if (c0 < 0 || (c0 & 3) || c0 + L.seg_cam > L.cam_pitch) return bad("camera segment", wt, 0, c0 + L.seg_cam, L.cam_pitch);
+        if (w_base + L.seg_cs > L.cs_pitch) return bad("camera statistics segment", wt, 0, w_base + L.seg_cs, L.cs_pitch);
+        int s_lo = 1 << 30, s_hi = -(1 << 30);
+        for (int c = 0; c < L.n_chunks; ++c) {
+            const int s_base = chunk_s_base(L, p.W, w_base, c);
+            const int x0 = w_base - L.r - s_base - L.SC + 1 + L.proj_lp, d0 = w_base - s_base - L.SC + 1 + L.ps_ld;
+            if (s_base & 3) return bad("chunk alignment", wt, c, s_base, 4);
+            if (x0 < 0 || (x0 & 3) || x0 + L.seg_proj > L.proj_pitch) return bad("projector segment", wt, c, x0 + L.seg_proj, L.proj_pitch);
+            if (d0 < 0 || (d0 & 3) || d0 + L.seg_ps > L.ps_pitch) return bad("projector statistics segment", wt, c, d0 + L.seg_ps, L.ps_pitch);
+            s_lo = std::min(s_lo, s_base); s_hi = std::max(s_hi, s_base + L.SC - 1);
+        }
+        // the chunks of a column tile cover every disparity any of its columns needs
+        const int need_lo = p.banded ? 0 : w_base - (p.W - 1), need_hi = p.banded ? p.D - 1 : std::min(w_base + L.WTC, p.W) - 1;
+        if (s_lo > need_lo || s_hi < need_hi) return bad("disparity coverage", wt, 0, s_lo, s_hi);
+    }
+    // the column of the copies that holds image column X = -r .. W-1+(K-1-r) of every statistics window exists
+    if (L.cam_lc < L.r || L.proj_lp < L.r) return bad("left apron", 0, 0, L.cam_lc, L.proj_lp);
+    if (L.cam_lc + p.W + L.K - 1 - L.r > L.cam_pitch + 0 && L.cam_pitch < p.W) return bad("camera pitch", 0, 0, L.cam_pitch, p.W);
+    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_maxabs_c, L.off_maxabs_p, L.zero_end, L.off_e2min_c, L.off_e2min_p,
+                           L.big_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
+                           L.off_ey2, L.off_extra, L.total};
+    for (size_t i = 1; i < sizeof(offs) / sizeof(offs[0]); ++i)
+        if (offs[i] < offs[i - 1] || (offs[i] & 255)) return bad("workspace offsets", (int)i, 0, (int)(offs[i] >> 8), (int)(offs[i - 1] >> 8));
+    return CUSTMA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     band_minmax_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,

@@ -62,6 +62,10 @@ const char *custma_last_error(void);
  * bench.py reports the per-step difference as "gpu_launches". */
 uint64_t custma_launch_count(void);
 
+/* Host-only self-check of the tiling the fast kernels would use for this problem (every shared-memory row segment inside
+ * its workspace row and 16-byte aligned, chunks covering every disparity, ...).  Needs no GPU.  0 = consistent. */
+int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size);
+
 /* Workspace (device memory, 256-byte aligned) the caller must provide; depends only on the arguments shown. */
 size_t custma_forward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
 size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
