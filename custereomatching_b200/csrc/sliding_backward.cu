@@ -12,11 +12,13 @@
 //
 // The main kernel marches down a row band like the forward does (same thread tile: 4 columns x 4 disparities, same
 // pair-sum ring to recompute exy), keeps a second ring for the vertical k-row sum of a, convolves it horizontally in
-// registers, multiplies by the projector row of the TARGET image row and reduces over the 16 lanes of a unit with a
-// shuffle reduce-scatter.  Per-unit partial sums go to shared memory and are added in a fixed order two steps later;
-// per-tile T1 rows and per-pixel Am / Bs go to the workspace, and sliding_backward_finalize_kernel gathers them.
+// registers (prefix / suffix sums), multiplies by the projector row of the TARGET image row and sums the 16 per-thread
+// partials over the 16 lanes of a unit through a shared-memory transpose (fixed summation tree).  Per-unit partial
+// sums are added in a fixed order four steps later; every tile stores its T1 rows directly into one of four dense
+// images chosen by (band parity, column-tile parity) - tiles of equal parities never overlap - and per-pixel Am / Bs go
+// to per-chunk images; sliding_backward_finalize_kernel gathers them.
 // The upstream gradient is prefetched with per-thread cp.async (each thread reads back only what it copied, so no
-// barrier is involved), three row steps ahead.
+// barrier is involved), up to three row steps ahead.
 #include "sliding_common.cuh"
 
 namespace custma {
