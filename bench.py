@@ -291,15 +291,15 @@ def run_b200(args):
     ggen = torch.Generator(device=device).manual_seed(1)
     grad_in = torch.randn(P, H, W, D, device=device, generator=ggen)
     cost = torch.empty(P, H, W, D, device=device)
-    best = torch.empty(P, H, W, device=device)
-    disp = torch.empty(P, H, W, dtype=torch.int32, device=device)
-    cam_grad = torch.empty(P, H, W, device=device)
+    # best / disparity / camera_grad share one buffer so that the results of a step leave in ONE all_gather
+    results = torch.empty(3, P, H, W, device=device)
+    best, cam_grad = results[0], results[2]
+    disp = results[1].view(torch.int32)
     ws_bytes = max(binding.forward_workspace_bytes(P, H, W, D, k, flags),
                    binding.backward_workspace_bytes(P, H, W, D, k, flags))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     if world > 1:
-        gather_f = torch.empty(2, world * P, H, W, device=device)           # best, camera_grad
-        gather_i = torch.empty(world * P, H, W, dtype=torch.int32, device=device)
+        gathered = torch.empty(world, 3, P, H, W, device=device)
     stream = torch.cuda.current_stream(device)
     sptr = stream.cuda_stream
 
@@ -312,10 +312,8 @@ def run_b200(args):
                          P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
 
     def gather():
-        if world > 1:   # results only: 3 * P*H*W*4 bytes per rank; the volume never leaves the GPU
-            dist.all_gather_into_tensor(gather_f[0], best)
-            dist.all_gather_into_tensor(gather_i, disp)
-            dist.all_gather_into_tensor(gather_f[1], cam_grad)
+        if world > 1:   # results only: 3 * P*H*W*4 bytes per rank in one collective; the volume never leaves the GPU
+            dist.all_gather_into_tensor(gathered, results)
 
     def step():
         fwd()
