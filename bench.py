@@ -271,8 +271,12 @@ def run_b200(args):
     binding.load()                                                   # fail loudly if the extension is missing
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL announces its version on stdout when
+    # NCCL_DEBUG is set in the environment) goes to stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")               # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     H, W, D, k, default_pairs, desc = WORKLOADS[args.workload]
@@ -291,15 +295,18 @@ def run_b200(args):
     ggen = torch.Generator(device=device).manual_seed(1)
     grad_in = torch.randn(P, H, W, D, device=device, generator=ggen)
     cost = torch.empty(P, H, W, D, device=device)
-    # best / disparity / camera_grad share one buffer so that the results of a step leave in ONE all_gather
-    results = torch.empty(3, P, H, W, device=device)
-    best, cam_grad = results[0], results[2]
+    # best and disparity share one buffer and leave in one all_gather that overlaps the backward kernels (NCCL runs it
+    # on its own stream); camera_grad follows in a second one
+    results = torch.empty(2, P, H, W, device=device)
+    best = results[0]
     disp = results[1].view(torch.int32)
+    cam_grad = torch.empty(P, H, W, device=device)
     ws_bytes = max(binding.forward_workspace_bytes(P, H, W, D, k, flags),
                    binding.backward_workspace_bytes(P, H, W, D, k, flags))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     if world > 1:
-        gathered = torch.empty(world, 3, P, H, W, device=device)
+        gathered = torch.empty(world, 2, P, H, W, device=device)
+        gathered_grad = torch.empty(world, P, H, W, device=device)
     stream = torch.cuda.current_stream(device)
     sptr = stream.cuda_stream
 
@@ -311,14 +318,13 @@ def run_b200(args):
         binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(),
                          P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
 
-    def gather():
-        if world > 1:   # results only: 3 * P*H*W*4 bytes per rank in one collective; the volume never leaves the GPU
-            dist.all_gather_into_tensor(gathered, results)
-
     def step():
         fwd()
-        bwd()
-        gather()
+        pending = dist.all_gather_into_tensor(gathered, results, async_op=True) if world > 1 else None
+        bwd()   # results only cross GPUs: 3 * P*H*W*4 bytes per rank; the volume never leaves its GPU
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_grad, cam_grad)
+            pending.wait()
 
     def barrier():
         if world > 1:
@@ -421,6 +427,9 @@ def run_b200(args):
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                "host_cpus": os.cpu_count()}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         line = {
             "metric": METRIC, "value": cells_job / ms_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": K,
