@@ -152,7 +152,7 @@ struct SumRing {
     }
 };
 
-template <int K, int NU, int WG, int MODE>
+template <int K, int NU, int WG, int MODE, int DIR>
 __device__ __forceinline__ void backward_consumer(const Problem &p, const SlidingLayout &L, float *smem,
                                                   uint64_t *full_bar, uint64_t *empty_bar,
                                                   BwdRowLoader<K, NU, WG> &loader, int b, int h0, int rows, int w_base,
@@ -263,7 +263,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             for (int v = 0; v < PL / 4; ++v)
                 *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
             float bx[4][4];
-            ring.step(q, c, pj, seed, bx);
+            ring.template step<DIR>(q, c, pj, seed, bx);
 
             float a4[4], e4[4], sp[8], ey[8], gg[4][4];
             *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
@@ -419,17 +419,19 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     for (int t = 0; t < kBwdLookahead && t < steps; ++t) loader.issue(t, smem, full_bar);
 
 
-    // bodies as in the forward: 0 = all cells valid, 1 = 16-byte gradient loads with a validity mask, 2 = scalar
+    // bodies as in the forward: MODE 0 = all cells valid, 1 = 16-byte gradient loads with a validity mask, 2 = scalar;
+    // DIR = direction of the sliding horizontal sums (towards the zero padding the tile can see, 0 = no sliding)
     const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
-    if (vec && w_base + WTC <= p.W && w_base - (s_base + SC - 1) >= 0)
-        backward_consumer<K, NU, WG, 0>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, BL.Wp, AmRow, BsRow);
-    else if (vec)
-        backward_consumer<K, NU, WG, 1>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, BL.Wp, AmRow, BsRow);
-    else
-        backward_consumer<K, NU, WG, 2>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps,
-                                        grad, T1tile, BL.Wp, AmRow, BsRow);
+    const bool clean_left = w_base > 0 && w_base - (s_base + SC - 1) - (K / 2 + 3) >= 0;
+    const bool clean_right = w_base + WTC + K <= p.W;
+#define CUSTMA_BWD_BODY(MODE, DIR)                                                                                      \
+    backward_consumer<K, NU, WG, MODE, DIR>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps, \
+                                            grad, T1tile, BL.Wp, AmRow, BsRow)
+    if (vec && clean_left && w_base + WTC <= p.W) CUSTMA_BWD_BODY(0, 1);
+    else if (vec && clean_right) CUSTMA_BWD_BODY(1, 2);
+    else if (vec) CUSTMA_BWD_BODY(1, 0);
+    else CUSTMA_BWD_BODY(2, 0);
+#undef CUSTMA_BWD_BODY
 }
 
 // camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of

@@ -47,8 +47,8 @@ struct SlidingLayout {
     // byte offsets into the workspace
     size_t off_minmax, off_camP, off_projP, off_A, off_ex2, off_Sp, off_ey2, off_wta, off_extra, total;
     // conditioning summaries per (pair, band, block of 16 columns) and the per-tile verdicts derived from them
-    int32_t nblk_camP, nblk_projP, nblk_cs, nblk_ps;
-    size_t off_maxabs_c, off_maxabs_p, off_e2min_c, off_e2min_p, off_flags, off_tileany, zero_end, big_end;
+    int32_t nblk_cs, nblk_ps;
+    size_t off_rho_c, off_rho_p, off_flags, off_tileany, zero_end;
 };
 
 // flags[tile] != 0: the tile is ill-conditioned for the O(1) window sums and is computed by the direct kernels
@@ -172,18 +172,32 @@ struct BoxRing {
                 for (int m = 0; m < K - 2; ++m) P[m][i][j] = 0.f;
             }
     }
-    // Q = t mod (K-2); a compile-time constant once the caller's row loop is unrolled by K-2
+    // Q = t mod (K-2); a compile-time constant once the caller's row loop is unrolled by K-2.
+    // DIR 1 / 2: the other three columns reuse the neighbouring column's sum (add the entering product, subtract the
+    // leaving one), sliding left-to-right (1) or right-to-left (2); DIR 0: every column gets its own k-term chain.
+    // Sliding carries the rounding of the leaving products into the next column.  That is harmless inside the image
+    // but not next to the zero padding, where a product with the padding value -pivot can be orders of magnitude
+    // larger than everything in the neighbouring windows - so the chain must always slide TOWARDS the padding: tiles
+    // at the left border (camera columns < 0, projector columns w - s < 0) slide right-to-left, the others
+    // left-to-right, and tiles that could see padding on both sides do not slide.
+    template <int DIR>
     __device__ __forceinline__ void step(const int Q, const float *c, const float *pj, float seed, float (&bx)[4][4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float s = fmaf(c[0], pj[3 - j], seed);
+            float s = 0.f;
 #pragma unroll
-            for (int x = 1; x < K; ++x) s = fmaf(c[x], pj[x + 3 - j], s);
+            for (int n = 0; n < 4; ++n) {
+                const int i = DIR == 2 ? 3 - n : n;
+                if (n == 0 || DIR == 0) {
+                    s = fmaf(c[i], pj[i + 3 - j], seed);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i > 0) {
+                    for (int x = 1; x < K; ++x) s = fmaf(c[i + x], pj[i + x + 3 - j], s);
+                } else if (DIR == 1) {
                     s = fmaf(c[i + K - 1], pj[i + K - 1 + 3 - j], s);
                     s = fmaf(-c[i - 1], pj[i - 1 + 3 - j], s);
+                } else {
+                    s = fmaf(c[i], pj[i + 3 - j], s);
+                    s = fmaf(-c[i + K], pj[i + K + 3 - j], s);
                 }
                 float box = s;
 #pragma unroll

@@ -20,7 +20,7 @@ namespace custma {
 
 
 
-template <int K, int NU, int WG, int MODE, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
@@ -58,19 +58,21 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     loader.init(L, ws, b, nb, h0, w_base, s_base);
     for (int t = 0; t < kLookahead && t < steps; ++t) loader.issue(t, smem, full_bar, empty_bar);
 
-    // Three bodies: 0 = every cell of the tile is valid (check-free, 128-bit stores); 1 = 128-bit stores with a
-    // per-thread validity mask (tiles that touch w - s < 0 or the right image border); 2 = scalar, fully checked
-    // (reference-shaped volume, D not a multiple of the chunk).
+    // Bodies: MODE 0 = every cell of the tile is valid (check-free, 128-bit stores); 1 = 128-bit stores with a per-thread
+    // validity mask (tiles that touch w - s < 0 or the right image border); 2 = scalar, fully checked (reference-shaped
+    // volume, D not a multiple of the chunk).  DIR = direction of the sliding horizontal sums (BoxRing::step): towards
+    // the zero padding a tile can see, or no sliding when that could be on both sides.
     const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
-    if (vec && w_base + WTC <= p.W && w_base - (s_base + SC - 1) >= 0)
-        forward_consumer<K, NU, WG, 0, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
-                                                  steps, cost, wta_keys);
-    else if (vec)
-        forward_consumer<K, NU, WG, 1, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
-                                                  steps, cost, wta_keys);
-    else
-        forward_consumer<K, NU, WG, 2, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,
-                                                  steps, cost, wta_keys);
+    const bool clean_left = w_base > 0 && w_base - (s_base + SC - 1) - (K / 2 + 3) >= 0;   // no padding left of any chain
+    const bool clean_right = w_base + WTC + K <= p.W;
+#define CUSTMA_FWD_BODY(MODE, DIR)                                                                                        \
+    forward_consumer<K, NU, WG, MODE, DIR, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,  \
+                                                      steps, cost, wta_keys)
+    if (vec && clean_left && w_base + WTC <= p.W) CUSTMA_FWD_BODY(0, 1);
+    else if (vec && clean_right) CUSTMA_FWD_BODY(1, 2);
+    else if (vec) CUSTMA_FWD_BODY(1, 0);
+    else CUSTMA_FWD_BODY(2, 0);
+#undef CUSTMA_FWD_BODY
 }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -78,7 +80,7 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 __device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-template <int K, int NU, int WG, int MODE, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
@@ -125,7 +127,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
             for (int v = 0; v < PL / 4; ++v)
                 *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
             float bx[4][4];
-            ring.step(q, c, pj, seed, bx);
+            ring.template step<DIR>(q, c, pj, seed, bx);
             if (t >= K - 1) {  // the first k-1 steps only fill the ring
                 float a4[4], e4[4], sp[8], ey[8];
                 *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);

@@ -82,18 +82,13 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     const size_t bands = (size_t)p.B * L->NB, rows = (size_t)p.B * L->NB * L->RB;
-    L->nblk_camP = (L->cam_pitch + 15) / 16; L->nblk_projP = (L->proj_pitch + 15) / 16;
     L->nblk_cs = (L->cs_pitch + 15) / 16; L->nblk_ps = (L->ps_pitch + 15) / 16;
-    // zero-initialised region (one memset): band min/max accumulators, WTA keys, max |pivoted value| per block
+    // zero-initialised region (one memset): band min/max accumulators, WTA keys, worst window conditioning per block
     L->off_minmax = take(2 * bands * 2 * sizeof(uint32_t));            // [img][pair*band][max(v), max(-v)] ordered
     L->off_wta = take((size_t)p.pixels() * sizeof(unsigned long long));  // packed (best, s) keys
-    L->off_maxabs_c = take(bands * L->nblk_camP * sizeof(float));
-    L->off_maxabs_p = take(bands * L->nblk_projP * sizeof(float));
+    L->off_rho_c = take(bands * L->nblk_cs * sizeof(float));
+    L->off_rho_p = take(bands * L->nblk_ps * sizeof(float));
     L->zero_end = off;
-    // "huge"-initialised region (memset 0x7f): min second moment per block
-    L->off_e2min_c = take(bands * L->nblk_cs * sizeof(float));
-    L->off_e2min_p = take(bands * L->nblk_ps * sizeof(float));
-    L->big_end = off;
     L->off_flags = take((size_t)p.B * L->NB * L->n_wtiles * L->n_chunks);
     L->off_tileany = take((size_t)p.B * L->NB * L->n_wtiles);
     L->off_camP = take(bands * L->RBH * L->cam_pitch * sizeof(float));
@@ -143,8 +138,7 @@ int validate_sliding_layout(const Problem &p, bool backward) {
     // the column of the copies that holds image column X = -r .. W-1+(K-1-r) of every statistics window exists
     if (L.cam_lc < L.r || L.proj_lp < L.r) return bad("left apron", 0, 0, L.cam_lc, L.proj_lp);
     if (L.cam_lc + p.W + L.K - 1 - L.r > L.cam_pitch + 0 && L.cam_pitch < p.W) return bad("camera pitch", 0, 0, L.cam_pitch, p.W);
-    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_maxabs_c, L.off_maxabs_p, L.zero_end, L.off_e2min_c, L.off_e2min_p,
-                           L.big_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
+    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.zero_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
                            L.off_ey2, L.off_extra, L.total};
     for (size_t i = 1; i < sizeof(offs) / sizeof(offs[0]); ++i)
         if (offs[i] < offs[i - 1] || (offs[i] & 255)) return bad("workspace offsets", (int)i, 0, (int)(offs[i] >> 8), (int)(offs[i - 1] >> 8));
@@ -193,11 +187,10 @@ __device__ __forceinline__ float band_pivot(const uint32_t *__restrict__ minmax,
     return isfinite(pv) ? pv : 0.f;
 }
 
-// four consecutive elements of the two band copies per thread; also max |pivoted value| per block of 16 columns
+// four consecutive elements of the two band copies per thread
 __global__ void __launch_bounds__(256)
     band_copy_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
-                     const uint32_t *__restrict__ minmax, float *__restrict__ camP, float *__restrict__ projP,
-                     float *__restrict__ maxabs_c, float *__restrict__ maxabs_p) {
+                     const uint32_t *__restrict__ minmax, float *__restrict__ camP, float *__restrict__ projP) {
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B;
     const int pitch = img ? L.proj_pitch : L.cam_pitch, left = img ? L.proj_lp : L.cam_lc;
     const int t = blockIdx.y % L.RBH, nb = blockIdx.y / L.RBH;
@@ -205,36 +198,34 @@ __global__ void __launch_bounds__(256)
     const float pv = band_pivot(minmax, p, L, img, b, nb);
     const float *row = (img ? proj : cam) + ((int64_t)b * p.H + y) * p.W;
     float *out = (img ? projP : camP) + (((int64_t)b * L.NB + nb) * L.RBH + t) * pitch;
-    float *mx = (img ? maxabs_p : maxabs_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_projP : L.nblk_camP);
     const bool yin = y >= 0 && y < p.H;
     const int ci = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    float m = 0.f;
     if (ci < pitch) {
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int x = ci + e - left;
             v[e] = ((yin && x >= 0 && x < p.W) ? __ldg(row + x) : 0.f) - pv;
-            m = fmaxf(m, fabsf(v[e]));
         }
         *reinterpret_cast<float4 *>(out + ci) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    if ((threadIdx.x & 3) == 0 && ci < pitch) atomicMax(reinterpret_cast<uint32_t *>(mx + ci / 16), __float_as_uint(m));
 }
 
 // Window statistics of the pivoted band copies: one thread per column marches down the band keeping the last k-1
-// horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  One-pass second moment
-// e2 = sum v^2 - (sum v)^2 / n on band-pivoted data: its error, eps * n * max|v|^2, is what the tile verdict bounds.
-// camera: A = window mean, ex2;   projector: Sp = window sum, ey2;   plus min e2 per block of 16 columns.
+// horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  The sums are accumulated in
+// double, so the one-pass second moment e2 = sum v^2 - (sum v)^2 / n is as accurate as a two-pass fp32 one whatever
+// the pivot (this kernel is image-sized: fp64 costs nothing here).
+// camera: A = window mean, ex2;   projector: Sp = window sum, ey2.
+// Conditioning of a window: rho = n * max|v|^2 / e2 (how much larger the raw sums are than what survives the
+// cancellation); the worst rho per block of 16 columns feeds the tile verdict.  rho = 0 for an exactly constant window
+// of pivoted zeros, infinite for any other flat window.
 constexpr int kStatRows = 16;   // output rows per thread of band_stats_kernel
 
 template <int K>
 __global__ void __launch_bounds__(128)
     band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ camP, const float *__restrict__ projP,
                       float *__restrict__ A, float *__restrict__ ex2, float *__restrict__ Sp,
-                      float *__restrict__ ey2, float *__restrict__ e2min_c, float *__restrict__ e2min_p) {
+                      float *__restrict__ ey2, float *__restrict__ rho_c, float *__restrict__ rho_p) {
     // blockIdx.y = band * segments + segment: a thread marches kStatRows output rows (+ k-1 warm-up rows) of one column
     const int nseg = (L.RB + kStatRows - 1) / kStatRows;
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y / nseg, seg = blockIdx.y % nseg;
@@ -244,57 +235,73 @@ __global__ void __launch_bounds__(128)
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = ci - left;
     const bool col_ok = ci < pitch && x >= 0 && x < p.W;
-    const float *src = (img ? projP : camP) + ((int64_t)b * L.NB + nb) * L.RBH * pitchP + (col_ok ? x - L.r + leftP : 0);
+    const int c0 = col_ok ? x - L.r + leftP : 0;   // column of the copy that holds image column x - r
+    const float *src = (img ? projP : camP) + ((int64_t)b * L.NB + nb) * L.RBH * pitchP + c0;
     float *o1 = (img ? Sp : A) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     float *o2 = (img ? ey2 : ex2) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     const float inv_n = 1.f / (float)(K * K);
-    float r1[K - 1], r2[K - 1];
+    double r1[K - 1], r2[K - 1];
+    float rm[K - 1];
 #pragma unroll
-    for (int m = 0; m < K - 1; ++m) r1[m] = r2[m] = 0.f;
-    float emin = 3.0e38f;
+    for (int m = 0; m < K - 1; ++m) { r1[m] = r2[m] = 0.0; rm[m] = 0.f; }
+    float rho = 0.f;
     for (int t = t_begin; t < t_end; ++t) {
-        float h1 = 0.f, h2 = 0.f;
+        double h1 = 0.0, h2 = 0.0;
+        float hm = 0.f;
         if (col_ok) {
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const float v = src[(int64_t)t * pitchP + j];
-                h1 += v;
-                h2 = fmaf(v, v, h2);
+                h1 += (double)v;
+                h2 = fma((double)v, (double)v, h2);
+                hm = fmaxf(hm, fabsf(v));
+            }
+            // the kernels slide the horizontal sum over a thread's 4 columns (add the entering product, subtract the
+            // leaving one), so a window also inherits the rounding of its up to 3 in-image neighbours on either side
+            // (tiles that can see the zero padding do not slide): take the magnitude over that span
+#pragma unroll
+            for (int j = 1; j <= 3; ++j) {
+                if (x - L.r - j >= 0) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP - j]));
+                if (x - L.r + K - 1 + j < p.W) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
             }
         }
-        float s1 = h1, s2 = h2;
+        double s1 = h1, s2 = h2;
+        float sm = hm;
 #pragma unroll
-        for (int m = 0; m < K - 1; ++m) { s1 += r1[m]; s2 += r2[m]; }
+        for (int m = 0; m < K - 1; ++m) { s1 += r1[m]; s2 += r2[m]; sm = fmaxf(sm, rm[m]); }
 #pragma unroll
-        for (int m = 0; m < K - 2; ++m) { r1[m] = r1[m + 1]; r2[m] = r2[m + 1]; }
-        r1[K - 2] = h1; r2[K - 2] = h2;
+        for (int m = 0; m < K - 2; ++m) { r1[m] = r1[m + 1]; r2[m] = r2[m + 1]; rm[m] = rm[m + 1]; }
+        r1[K - 2] = h1; r2[K - 2] = h2; rm[K - 2] = hm;
         const int hr = t - (K - 1);
         if (hr >= t_begin && ci < pitch) {
             const bool ok = col_ok && nb * L.RB + hr < p.H;
-            const float mean = s1 * inv_n;
-            const float e2 = fmaxf(fmaf(-s1, mean, s2), 0.f);
+            const double mean = s1 * (double)inv_n;
+            const float e2 = (float)fmax(fma(-s1, mean, s2), 0.0);
             // neutral values elsewhere: they only ever meet masked cells
-            o1[(int64_t)hr * pitch] = ok ? (img ? s1 : mean) : 0.f;
+            o1[(int64_t)hr * pitch] = ok ? (float)(img ? s1 : mean) : 0.f;
             o2[(int64_t)hr * pitch] = ok ? e2 : 1.f;
-            if (ok) emin = fminf(emin, e2);
+            if (ok && sm > 0.f) rho = fmaxf(rho, (float)(K * K) * sm * sm / e2);   // e2 == 0 -> inf
         }
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+    for (int o = 8; o > 0; o >>= 1) rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
     if ((threadIdx.x & 15) == 0 && ci < pitch) {
-        float *mn = (img ? e2min_p : e2min_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_ps : L.nblk_cs) + ci / 16;
-        atomicMin(reinterpret_cast<uint32_t *>(mn), __float_as_uint(emin));   // non-negative floats order like uints
+        float *mx = (img ? rho_p : rho_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_ps : L.nblk_cs) + ci / 16;
+        atomicMax(reinterpret_cast<uint32_t *>(mx), __float_as_uint(rho));   // non-negative floats (and +inf) order like uints
     }
 }
 
-// Verdict per tile: is the fp32 error of the raw window sums, eps * n * max|cam'| * max|proj'| (and the same for the
-// one-pass second moments), safely below 1e-5 of the normalisation sqrt(ex2 * ey2 + eps) everywhere in the tile?
-// Tiles that fail (low contrast against the band pivot, image borders of images with a large DC level, ...) are left
-// to the direct two-pass kernels, which follow the reference's arithmetic order.
+// Verdict per tile.  The raw window sum of a cell loses, relative to the normalisation sqrt(ex2 * ey2), about
+//   eps_f32 * c * n * max|cam'| * max|proj'| / sqrt(ex2 * ey2) = eps_f32 * c * sqrt(rho_cam * rho_proj),
+// c ~ 1 for the statistical worst case over millions of cells (measured: 5e-7 at sqrt(rho_cam * rho_proj) = 6).
+// Tiles where the worst camera window (over the tile) and the worst projector window (over the tile's disparity
+// footprint) keep this below ~3e-6 run the fast kernels; the others (low contrast against the band pivot, flat
+// regions) are left to the direct two-pass kernels, which follow the reference's arithmetic order.
+constexpr float kMaxConditioning = 40.f;
+
 __global__ void __launch_bounds__(128)
-    tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ maxabs_c,
-                      const float *__restrict__ maxabs_p, const float *__restrict__ e2min_c,
-                      const float *__restrict__ e2min_p, uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany) {
+    tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ rho_c, const float *__restrict__ rho_p,
+                      uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
     if (id >= ntiles) return;
@@ -302,18 +309,13 @@ __global__ void __launch_bounds__(128)
     const int64_t band = (int64_t)b * L.NB + nb;
     const int w_base = wt * L.WTC;
     auto range_max = [](const float *a, int lo, int hi) { float m = 0.f; for (int i = lo / 16; i <= (hi - 1) / 16; ++i) m = fmaxf(m, a[i]); return m; };
-    auto range_min = [](const float *a, int lo, int hi) { float m = 3.0e38f; for (int i = lo / 16; i <= (hi - 1) / 16; ++i) m = fminf(m, a[i]); return m; };
-    const float cm = range_max(maxabs_c + band * L.nblk_camP, w_base - L.r + L.cam_lc, w_base - L.r + L.cam_lc + L.seg_cam);
-    const float e2c = range_min(e2min_c + band * L.nblk_cs, w_base, w_base + L.WTC);
-    const float coef = 6.0e-8f * 3.f * (float)(p.k * p.k);
+    const float rc = range_max(rho_c + band * L.nblk_cs, w_base, w_base + L.WTC);
     uint8_t any = 0;
     for (int ch = 0; ch < L.n_chunks; ++ch) {
         const int s_base = chunk_s_base(L, p.W, w_base, ch);
-        const int xlo = w_base - L.r - s_base - L.SC + 1, dlo = w_base - s_base - L.SC + 1;
-        const float pm = range_max(maxabs_p + band * L.nblk_projP, xlo + L.proj_lp, xlo + L.proj_lp + L.seg_proj);
-        const float e2p = range_min(e2min_p + band * L.nblk_ps, dlo + L.ps_ld, dlo + L.ps_ld + L.seg_ps);
-        const bool fast = coef * cm * pm <= 3.0e-6f * sqrtf(e2c * e2p + kEps) && coef * cm * cm <= 6.0e-6f * e2c &&
-                          coef * pm * pm <= 6.0e-6f * e2p;
+        const int dlo = w_base - s_base - L.SC + 1;
+        const float rp = range_max(rho_p + band * L.nblk_ps, dlo + L.ps_ld, dlo + L.ps_ld + L.seg_ps);
+        const bool fast = sqrtf(rc) * sqrtf(rp) <= kMaxConditioning;   // (not sqrtf(rc * rp): inf * 0 must flag)
         flags[id * L.n_chunks + ch] = fast ? 0 : 1;
         any |= fast ? 0 : 1;
     }
@@ -324,10 +326,8 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
                         cudaStream_t stream) {
     uint32_t *minmax = (uint32_t *)(ws + L.off_minmax);
     float *camP = (float *)(ws + L.off_camP), *projP = (float *)(ws + L.off_projP);
-    float *maxabs_c = (float *)(ws + L.off_maxabs_c), *maxabs_p = (float *)(ws + L.off_maxabs_p);
-    float *e2min_c = (float *)(ws + L.off_e2min_c), *e2min_p = (float *)(ws + L.off_e2min_p);
+    float *rho_c = (float *)(ws + L.off_rho_c), *rho_p = (float *)(ws + L.off_rho_p);
     CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.off_minmax, 0, L.zero_end - L.off_minmax, stream));
-    CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.zero_end, 0x7f, L.big_end - L.zero_end, stream));
     {
         const int64_t n = (int64_t)L.RBH * p.W;
         dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, 2 * p.B);
@@ -336,20 +336,20 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
     }
     {
         dim3 grid((std::max(L.cam_pitch, L.proj_pitch) / 4 + 255) / 256, L.NB * L.RBH, 2 * p.B);
-        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, camP, projP, maxabs_c, maxabs_p);
+        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, camP, projP);
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
         dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB * ((L.RB + kStatRows - 1) / kStatRows), 2 * p.B);
         auto kern = p.k == 3 ? band_stats_kernel<3> : p.k == 5 ? band_stats_kernel<5> : band_stats_kernel<7>;
         kern<<<grid, 128, 0, stream>>>(p, L, camP, projP, (float *)(ws + L.off_A), (float *)(ws + L.off_ex2),
-                                       (float *)(ws + L.off_Sp), (float *)(ws + L.off_ey2), e2min_c, e2min_p);
+                                       (float *)(ws + L.off_Sp), (float *)(ws + L.off_ey2), rho_c, rho_p);
         CUSTMA_LAUNCH_CHECK("band_stats_kernel");
     }
     {
         const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
         tile_flags_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, stream>>>(
-            p, L, maxabs_c, maxabs_p, e2min_c, e2min_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany));
+            p, L, rho_c, rho_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany));
         CUSTMA_LAUNCH_CHECK("tile_flags_kernel");
     }
     return CUSTMA_OK;
