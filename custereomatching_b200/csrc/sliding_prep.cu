@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // Window statistics of the pivoted band copies: one thread per column marches down the band keeping the last k-1
-// horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  The sums are accumulated in
-// double, so the one-pass second moment e2 = sum v^2 - (sum v)^2 / n is as accurate as a two-pass fp32 one whatever
-// the pivot (this kernel is image-sized: fp64 costs nothing here).
+// horizontal k-sums of v and v*v in registers (O(k) loads per pixel instead of k*k).  Every thread sums its own
+// windows, so it may shift the data by its own constant: it uses a pixel next to its first window, which keeps the
+// one-pass second moment e2 = sum u^2 - (sum u)^2 / n (u = v - shift) accurate in fp32 however far the band pivot is
+// from the local brightness; the window sum relative to the band pivot is recovered as sum u + n * shift.
 // camera: A = window mean, ex2;   projector: Sp = window sum, ey2.
 // Conditioning of a window: rho = n * max|v|^2 / e2 (how much larger the raw sums are than what survives the
 // cancellation); the worst rho per block of 16 columns feeds the tile verdict.  rho = 0 for an exactly constant window
@@ -240,20 +241,19 @@ __global__ void __launch_bounds__(128)
     float *o1 = (img ? Sp : A) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     float *o2 = (img ? ey2 : ex2) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     const float inv_n = 1.f / (float)(K * K);
-    double r1[K - 1], r2[K - 1];
-    float rm[K - 1];
+    float r1[K - 1], r2[K - 1], rm[K - 1];
 #pragma unroll
-    for (int m = 0; m < K - 1; ++m) { r1[m] = r2[m] = 0.0; rm[m] = 0.f; }
+    for (int m = 0; m < K - 1; ++m) r1[m] = r2[m] = rm[m] = 0.f;
+    const float shift = col_ok ? src[(int64_t)min(t_begin + K / 2, L.RBH - 1) * pitchP + K / 2] : 0.f;
     float rho = 0.f;
     for (int t = t_begin; t < t_end; ++t) {
-        double h1 = 0.0, h2 = 0.0;
-        float hm = 0.f;
+        float h1 = 0.f, h2 = 0.f, hm = 0.f;
         if (col_ok) {
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                const float v = src[(int64_t)t * pitchP + j];
-                h1 += (double)v;
-                h2 = fma((double)v, (double)v, h2);
+                const float v = src[(int64_t)t * pitchP + j], u = v - shift;
+                h1 += u;
+                h2 = fmaf(u, u, h2);
                 hm = fmaxf(hm, fabsf(v));
             }
             // the kernels slide the horizontal sum over a thread's 4 columns (add the entering product, subtract the
@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(128)
                 if (x - L.r + K - 1 + j < p.W) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
             }
         }
-        double s1 = h1, s2 = h2;
-        float sm = hm;
+        float s1 = h1, s2 = h2, sm = hm;
 #pragma unroll
         for (int m = 0; m < K - 1; ++m) { s1 += r1[m]; s2 += r2[m]; sm = fmaxf(sm, rm[m]); }
 #pragma unroll
@@ -275,10 +274,10 @@ __global__ void __launch_bounds__(128)
         const int hr = t - (K - 1);
         if (hr >= t_begin && ci < pitch) {
             const bool ok = col_ok && nb * L.RB + hr < p.H;
-            const double mean = s1 * (double)inv_n;
-            const float e2 = (float)fmax(fma(-s1, mean, s2), 0.0);
+            const float e2 = fmaxf(fmaf(-s1, s1 * inv_n, s2), 0.f);
+            const float sum = fmaf((float)(K * K), shift, s1);   // window sum of v (relative to the band pivot)
             // neutral values elsewhere: they only ever meet masked cells
-            o1[(int64_t)hr * pitch] = ok ? (float)(img ? s1 : mean) : 0.f;
+            o1[(int64_t)hr * pitch] = ok ? (img ? sum : sum * inv_n) : 0.f;
             o2[(int64_t)hr * pitch] = ok ? e2 : 1.f;
             if (ok && sm > 0.f) rho = fmaxf(rho, (float)(K * K) * sm * sm / e2);   // e2 == 0 -> inf
         }
