@@ -48,7 +48,8 @@ struct SlidingLayout {
     size_t off_minmax, off_camP, off_projP, off_A, off_ex2, off_Sp, off_ey2, off_wta, off_extra, total;
     // conditioning summaries per (pair, band, block of 16 columns) and the per-tile verdicts derived from them
     int32_t nblk_cs, nblk_ps;
-    size_t off_rho_c, off_rho_p, off_flags, off_tileany, zero_end;
+    size_t off_rho_c, off_rho_p, off_bandany, off_flags, off_tileany, zero_end;
+    size_t off_fb_pm, off_fb_ey2;   // per-pixel projector window mean / second moment for the fallback kernels
 };
 
 // flags[tile] != 0: the tile is ill-conditioned for the O(1) window sums and is computed by the direct kernels

@@ -42,27 +42,47 @@ __device__ __forceinline__ float warp_camera_patch(const Problem &p, const float
     return e2;
 }
 
-// projector window of column d: mean, then centred moments against the camera patch (reference :40-70)
-__device__ __forceinline__ void cell_moments(const Problem &p, const float *proj_plane, const float *camc, int h, int d,
-                                             float *pm_out, float *exy_out, float *ey2_out) {
+// Projector window statistics (mean over k*k including the zero padding, centred second moment: reference :40-70) of
+// every pixel of the bands that hold a flagged tile.  They do not depend on the camera column, so computing them once
+// per pixel instead of once per cell makes the fallback three times cheaper.
+__global__ void __launch_bounds__(256)
+    fallback_proj_stats_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ proj,
+                               const uint32_t *__restrict__ bandany, float *__restrict__ pm_out,
+                               float *__restrict__ ey2_out) {
+    const int h = blockIdx.y, b = blockIdx.z;
+    if (!bandany[b * L.NB + h / L.RB]) return;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= p.W) return;
+    const float *plane = proj + (int64_t)b * p.H * p.W;
     float pm = 0.f;
     for (int i = 0; i < p.k; ++i)
-        for (int j = 0; j < p.k; ++j) pm += query_ij(proj_plane, p.H, p.W, h + i - p.r, d + j - p.r);
+        for (int j = 0; j < p.k; ++j) pm += query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r);
     pm /= (float)(p.k * p.k);
-    float exy = 0.f, ey2 = 0.f;
+    float ey2 = 0.f;
     for (int i = 0; i < p.k; ++i)
         for (int j = 0; j < p.k; ++j) {
-            const float q = query_ij(proj_plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm;
-            exy = fmaf(camc[i * p.k + j], q, exy);
+            const float q = query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm;
             ey2 = fmaf(q, q, ey2);
         }
-    *pm_out = pm; *exy_out = exy; *ey2_out = ey2;
+    const int64_t o = ((int64_t)b * p.H + h) * p.W + d;
+    pm_out[o] = pm;
+    ey2_out[o] = ey2;
+}
+
+// centred correlation of the camera patch with the projector window of column d (reference :56-70)
+__device__ __forceinline__ float cell_exy(const Problem &p, const float *proj_plane, const float *camc, int h, int d, float pm) {
+    float exy = 0.f;
+    for (int i = 0; i < p.k; ++i)
+        for (int j = 0; j < p.k; ++j)
+            exy = fmaf(camc[i * p.k + j], query_ij(proj_plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm, exy);
+    return exy;
 }
 
 __global__ void __launch_bounds__(kFbWarps * 32)
     fallback_forward_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ cam,
                             const float *__restrict__ proj, const uint8_t *__restrict__ flags,
-                            const uint8_t *__restrict__ tileany, float *__restrict__ cost,
+                            const uint8_t *__restrict__ tileany, const float *__restrict__ fb_pm,
+                            const float *__restrict__ fb_ey2, float *__restrict__ cost,
                             unsigned long long *__restrict__ keys) {
     extern __shared__ float smem[];
     const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
@@ -86,9 +106,9 @@ __global__ void __launch_bounds__(kFbWarps * 32)
             const int d = p.banded ? w - c : c;
             float v = kInvalid;
             if (d >= 0) {
-                float pm, exy, ey2;
-                cell_moments(p, proj_plane, camc, h, d, &pm, &exy, &ey2);
-                v = (exy + kEps) / sqrtf(fmaf(ex2, ey2, kEps));   // reference :71
+                const int64_t o = ((int64_t)b * p.H + h) * p.W + d;
+                const float exy = cell_exy(p, proj_plane, camc, h, d, fb_pm[o]);
+                v = (exy + kEps) / sqrtf(fmaf(ex2, fb_ey2[o], kEps));   // reference :71
                 const int s = w - d;
                 if (v > bv || (v == bv && s > bs)) { bv = v; bs = s; }
             }
@@ -112,6 +132,7 @@ __global__ void __launch_bounds__(kFbWarps * 32)
     fallback_patch_grad_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ grad,
                                const float *__restrict__ cam, const float *__restrict__ proj,
                                const uint8_t *__restrict__ flags, const uint8_t *__restrict__ tileany,
+                               const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
                                float *__restrict__ patch_grad) {
     extern __shared__ float smem[];
     const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
@@ -134,8 +155,10 @@ __global__ void __launch_bounds__(kFbWarps * 32)
             const int d = p.banded ? w - c : c;
             float a = 0.f, pm = 0.f;
             if (d >= 0 && fl[cell_chunk(p, L, w_base, w, c)]) {
-                float exy, ey2;
-                cell_moments(p, proj_plane, camc, h, d, &pm, &exy, &ey2);
+                const int64_t o = ((int64_t)b * p.H + h) * p.W + d;
+                pm = fb_pm[o];
+                const float ey2 = fb_ey2[o];
+                const float exy = cell_exy(p, proj_plane, camc, h, d, pm);
                 const float den = sqrtf(fmaf(ex2, ey2, kEps));
                 const float g = grad[pix * p.C + c];
                 a = g / den;                                          // reference :135,:145
@@ -166,12 +189,25 @@ __global__ void __launch_bounds__(kFbWarps * 32)
     }
 }
 
+static int launch_fallback_proj_stats(const Problem &p, const SlidingLayout &L, const float *proj, const char *ws,
+                                      cudaStream_t stream) {
+    dim3 grid((p.W + 255) / 256, p.H, p.B);
+    fallback_proj_stats_kernel<<<grid, 256, 0, stream>>>(p, L, proj, (const uint32_t *)(ws + L.off_bandany),
+                                                         (float *)(const_cast<char *>(ws) + L.off_fb_pm),
+                                                         (float *)(const_cast<char *>(ws) + L.off_fb_ey2));
+    CUSTMA_LAUNCH_CHECK("fallback_proj_stats_kernel");
+    return CUSTMA_OK;
+}
+
 int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
                             const char *ws, float *cost, unsigned long long *keys, cudaStream_t stream) {
+    int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
+    if (rc) return rc;
     dim3 grid(L.n_wtiles, L.NB, p.B);
     const size_t smem = (size_t)kFbWarps * p.k * p.k * sizeof(float);
-    fallback_forward_kernel<<<grid, kFbWarps * 32, smem, stream>>>(p, L, cam, proj, (const uint8_t *)(ws + L.off_flags),
-                                                                   (const uint8_t *)(ws + L.off_tileany), cost, keys);
+    fallback_forward_kernel<<<grid, kFbWarps * 32, smem, stream>>>(
+        p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany),
+        (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost, keys);
     CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
     return CUSTMA_OK;
 }
@@ -186,8 +222,11 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback backward: last axis %d too long for shared memory", p.C);
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(fallback_patch_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)std::max<size_t>(smem, 48 * 1024)));
+    int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
+    if (rc) return rc;
     fallback_patch_grad_kernel<<<grid, kFbWarps * 32, smem, stream>>>(
-        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany), patch_grad);
+        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany),
+        (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), patch_grad);
     CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");
     return CUSTMA_OK;
 }

@@ -88,6 +88,7 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->off_wta = take((size_t)p.pixels() * sizeof(unsigned long long));  // packed (best, s) keys
     L->off_rho_c = take(bands * L->nblk_cs * sizeof(float));
     L->off_rho_p = take(bands * L->nblk_ps * sizeof(float));
+    L->off_bandany = take(bands * sizeof(uint32_t));                    // does the band hold a flagged tile?
     L->zero_end = off;
     L->off_flags = take((size_t)p.B * L->NB * L->n_wtiles * L->n_chunks);
     L->off_tileany = take((size_t)p.B * L->NB * L->n_wtiles);
@@ -97,6 +98,8 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->off_ex2 = take(rows * L->cs_pitch * sizeof(float));
     L->off_Sp = take(rows * L->ps_pitch * sizeof(float));
     L->off_ey2 = take(rows * L->ps_pitch * sizeof(float));
+    L->off_fb_pm = take((size_t)p.pixels() * sizeof(float));
+    L->off_fb_ey2 = take((size_t)p.pixels() * sizeof(float));
     L->off_extra = off;
     L->total = off;
 }
@@ -138,8 +141,8 @@ int validate_sliding_layout(const Problem &p, bool backward) {
     // the column of the copies that holds image column X = -r .. W-1+(K-1-r) of every statistics window exists
     if (L.cam_lc < L.r || L.proj_lp < L.r) return bad("left apron", 0, 0, L.cam_lc, L.proj_lp);
     if (L.cam_lc + p.W + L.K - 1 - L.r > L.cam_pitch + 0 && L.cam_pitch < p.W) return bad("camera pitch", 0, 0, L.cam_pitch, p.W);
-    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.zero_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
-                           L.off_ey2, L.off_extra, L.total};
+    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.off_bandany, L.zero_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
+                           L.off_ey2, L.off_fb_pm, L.off_fb_ey2, L.off_extra, L.total};
     for (size_t i = 1; i < sizeof(offs) / sizeof(offs[0]); ++i)
         if (offs[i] < offs[i - 1] || (offs[i] & 255)) return bad("workspace offsets", (int)i, 0, (int)(offs[i] >> 8), (int)(offs[i - 1] >> 8));
     return CUSTMA_OK;
@@ -300,7 +303,7 @@ constexpr float kMaxConditioning = 40.f;
 
 __global__ void __launch_bounds__(128)
     tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ rho_c, const float *__restrict__ rho_p,
-                      uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany) {
+                      uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany, uint32_t *__restrict__ bandany) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
     if (id >= ntiles) return;
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(128)
         any |= fast ? 0 : 1;
     }
     tileany[id] = any;
+    if (any) atomicOr(bandany + band, 1u);
 }
 
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
@@ -348,7 +352,8 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
     {
         const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
         tile_flags_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, stream>>>(
-            p, L, rho_c, rho_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany));
+            p, L, rho_c, rho_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany),
+            (uint32_t *)(ws + L.off_bandany));
         CUSTMA_LAUNCH_CHECK("tile_flags_kernel");
     }
     return CUSTMA_OK;
