@@ -87,7 +87,7 @@ struct BwdRowLoader {
             dst[n] = off < G::OFF_STG ? off : -1;
             if (off < G::OFF_PROJ) {
                 first[n] = 0; last[n] = L.RBH; stride[n] = L.cam_pitch;
-                src[n] = (const float *)(ws + L.off_camP) + band * L.RBH * L.cam_pitch + (w_base - F::r + L.cam_lc) + off;
+                src[n] = (const float *)(ws + L.off_camP) + band * L.RBH * L.cam_pitch + (w_base / F::WTC) * F::SEG_CAM + off;
             } else if (off < G::OFF_PROJT) {
                 first[n] = 0; last[n] = L.RBH; stride[n] = L.proj_pitch;
                 src[n] = (const float *)(ws + L.off_projP) + band * L.RBH * L.proj_pitch + (xlo + L.proj_lp) + (off - G::OFF_PROJ);
@@ -522,22 +522,26 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             }
         }
     }
-    // ---- per-pixel terms: cell rows h = y + r - i, i < k; row h = y + r - i is in band nbA unless i > ry
+    // ---- per-pixel terms: cell rows h = y + r - i (band nbA unless i > ry), cell columns w = x + r - j (column tile wtA
+    // unless j > rx); cam' and A of a cell are relative to the pivot of the cell's own tile
     float sub = 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const int h = y - i + r;
         if (h < 0 || h >= p.H) continue;
         const int nb = i <= ry ? nbA : nbA - 1;
-        const float cv = camP[(nb * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch + x + L.cam_lc];
+        const float *crow = camP + (nb * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch;
+        const float cvA = wtA < L.n_wtiles ? crow[wtA * L.seg_cam + (x - (wtA * L.WTC - r))] : 0.f;
+        const float cvB = wtA > 0 ? crow[(wtA - 1) * L.seg_cam + (x - ((wtA - 1) * L.WTC - r))] : 0.f;
         const int hh = threadIdx.y + K - 1 - i;
-        float s1 = 0.f, s2 = 0.f;
+        float s1 = 0.f, s2A = 0.f, s2B = 0.f;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             s1 += q1[hh][threadIdx.x + K - 1 - j];
-            s2 += q2[hh][threadIdx.x + K - 1 - j];
+            if (j <= rx) s2A += q2[hh][threadIdx.x + K - 1 - j];
+            else s2B += q2[hh][threadIdx.x + K - 1 - j];
         }
-        sub += fmaf(cv, s2, s1);
+        sub += fmaf(cvA, s2A, fmaf(cvB, s2B, s1));
     }
     acc -= sub;
     if (flagged_near) {   // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178 as a gather)

@@ -39,7 +39,9 @@ struct SlidingLayout {
     int32_t RB, RBH, NB;          // rows per band, rows of a band copy (RB + K - 1), number of bands
     int32_t n_wtiles, n_chunks;   // column tiles, disparity chunks per column tile
     int32_t banded, smin_full;    // full mode: chunk c of tile wt starts at rounddown4(w_base - (W-1)) + c*SC
-    int32_t cam_lc, cam_pitch;    // pivoted camera copy: [B][NB][RBH][cam_pitch], column x at index x + cam_lc
+    int32_t cam_lc, cam_pitch;    // pivoted camera copy: [B][NB][RBH][cam_pitch], tile-major: tile wt holds image
+                                  // columns wt*WTC - r + j at index wt*seg_cam + j (j < seg_cam), shifted by the
+                                  // tile's own pivot; cam_lc is unused (kept 0)
     int32_t proj_lp, proj_pitch;  // pivoted projector copy: [B][NB][RBH][proj_pitch], column X at index X + proj_lp
     int32_t cs_pitch;             // camera statistics  [B][NB*RB][cs_pitch]   (A = window sum / k^2, ex2)
     int32_t ps_ld, ps_pitch;      // projector statistics [B][NB*RB][ps_pitch], column d at index d + ps_ld (Sp, ey2)
@@ -49,6 +51,7 @@ struct SlidingLayout {
     // conditioning summaries per (pair, band, block of 16 columns) and the per-tile verdicts derived from them
     int32_t nblk_cs, nblk_ps;
     size_t off_rho_c, off_rho_p, off_bandany, off_flags, off_tileany, zero_end;
+    size_t off_campiv;              // camera pivot per (pair, band, column tile)
     size_t off_fb_pm, off_fb_ey2;   // per-pixel projector window mean / second moment for the fallback kernels
 };
 
@@ -235,7 +238,7 @@ struct RowLoader {
             first[n] = off < G::OFF_A ? 0 : K - 1;
             if (off < G::OFF_PROJ) {
                 stride[n] = L.cam_pitch;
-                src[n] = (const float *)(ws + L.off_camP) + band * L.RBH * L.cam_pitch + (w_base - G::r + L.cam_lc) + off;
+                src[n] = (const float *)(ws + L.off_camP) + band * L.RBH * L.cam_pitch + (w_base / G::WTC) * G::SEG_CAM + off;
             } else if (off < G::OFF_A) {
                 stride[n] = L.proj_pitch;
                 src[n] = (const float *)(ws + L.off_projP) + band * L.RBH * L.proj_pitch + (xlo + L.proj_lp) + (off - G::OFF_PROJ);

@@ -62,8 +62,8 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->seg_cam = cfg.seg_cam(); L->seg_proj = cfg.seg_proj(); L->seg_cs = cfg.seg_cs(); L->seg_ps = cfg.seg_ps();
     L->slot_floats = L->seg_cam + L->seg_proj + 2 * L->seg_cs + 2 * L->seg_ps;
 
-    L->cam_lc = L->r;                                                 // column w_base - r sits at index w_base: 16-byte aligned
-    L->cam_pitch = roundup4((L->n_wtiles - 1) * L->WTC - L->r + L->cam_lc + L->seg_cam);
+    L->cam_lc = 0;
+    L->cam_pitch = L->n_wtiles * L->seg_cam;                          // tile-major, seg_cam is a multiple of 4
     int min_xlo = 0, max_xhi = 0, min_dlo = 0, max_dhi = 0;
     for (int wt = 0; wt < L->n_wtiles; ++wt)
         for (int c = 0; c < L->n_chunks; ++c) {
@@ -86,12 +86,13 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     // zero-initialised region (one memset): band min/max accumulators, WTA keys, worst window conditioning per block
     L->off_minmax = take(2 * bands * 2 * sizeof(uint32_t));            // [img][pair*band][max(v), max(-v)] ordered
     L->off_wta = take((size_t)p.pixels() * sizeof(unsigned long long));  // packed (best, s) keys
-    L->off_rho_c = take(bands * L->nblk_cs * sizeof(float));
+    L->off_rho_c = take(bands * L->n_wtiles * sizeof(float));          // per column tile
     L->off_rho_p = take(bands * L->nblk_ps * sizeof(float));
     L->off_bandany = take(bands * sizeof(uint32_t));                    // does the band hold a flagged tile?
     L->zero_end = off;
     L->off_flags = take((size_t)p.B * L->NB * L->n_wtiles * L->n_chunks);
     L->off_tileany = take((size_t)p.B * L->NB * L->n_wtiles);
+    L->off_campiv = take((size_t)p.B * L->NB * L->n_wtiles * sizeof(float));
     L->off_camP = take(bands * L->RBH * L->cam_pitch * sizeof(float));
     L->off_projP = take(bands * L->RBH * L->proj_pitch * sizeof(float));
     L->off_A = take(rows * L->cs_pitch * sizeof(float));
@@ -122,8 +123,9 @@ int validate_sliding_layout(const Problem &p, bool backward) {
     if (L.n_wtiles * L.WTC < p.W) return bad("column tiles", 0, 0, L.n_wtiles * L.WTC, p.W);
     for (int wt = 0; wt < L.n_wtiles; ++wt) {
         const int w_base = wt * L.WTC;
-        const int c0 = w_base - L.r + L.cam_lc;
-        if (c0 < 0 || (c0 & 3) || c0 + L.seg_cam > L.cam_pitch) return bad("camera segment", wt, 0, c0 + L.seg_cam, L.cam_pitch);
+        const int c0 = wt * L.seg_cam;
+        if ((c0 & 3) || c0 + L.seg_cam > L.cam_pitch) return bad("camera segment", wt, 0, c0 + L.seg_cam, L.cam_pitch);
+        if (L.seg_cam < L.WTC + L.K - 1) return bad("camera segment width", wt, 0, L.seg_cam, L.WTC + L.K - 1);
         if (w_base + L.seg_cs > L.cs_pitch) return bad("camera statistics segment", wt, 0, w_base + L.seg_cs, L.cs_pitch);
         int s_lo = 1 << 30, s_hi = -(1 << 30);
         for (int c = 0; c < L.n_chunks; ++c) {
@@ -139,9 +141,8 @@ int validate_sliding_layout(const Problem &p, bool backward) {
         if (s_lo > need_lo || s_hi < need_hi) return bad("disparity coverage", wt, 0, s_lo, s_hi);
     }
     // the column of the copies that holds image column X = -r .. W-1+(K-1-r) of every statistics window exists
-    if (L.cam_lc < L.r || L.proj_lp < L.r) return bad("left apron", 0, 0, L.cam_lc, L.proj_lp);
-    if (L.cam_lc + p.W + L.K - 1 - L.r > L.cam_pitch + 0 && L.cam_pitch < p.W) return bad("camera pitch", 0, 0, L.cam_pitch, p.W);
-    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.off_bandany, L.zero_end, L.off_flags, L.off_tileany, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
+    if (L.proj_lp < L.r) return bad("left apron", 0, 0, L.proj_lp, L.r);
+    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.off_bandany, L.zero_end, L.off_flags, L.off_tileany, L.off_campiv, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
                            L.off_ey2, L.off_fb_pm, L.off_fb_ey2, L.off_extra, L.total};
     for (size_t i = 1; i < sizeof(offs) / sizeof(offs[0]); ++i)
         if (offs[i] < offs[i - 1] || (offs[i] & 255)) return bad("workspace offsets", (int)i, 0, (int)(offs[i] >> 8), (int)(offs[i - 1] >> 8));
@@ -150,10 +151,9 @@ int validate_sliding_layout(const Problem &p, bool backward) {
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    band_minmax_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
-                       uint32_t *__restrict__ minmax) {
-    const int nb = blockIdx.y, img = blockIdx.z / p.B, b = blockIdx.z % p.B;
-    const float *plane = (img ? proj : cam) + (int64_t)b * p.H * p.W;
+    band_minmax_kernel(Problem p, SlidingLayout L, const float *__restrict__ proj, uint32_t *__restrict__ minmax) {
+    const int nb = blockIdx.y, img = 1, b = blockIdx.z;   // projector only: the camera has one pivot per column tile
+    const float *plane = proj + (int64_t)b * p.H * p.W;
     const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RB + L.K - 1 - L.r);
     const int64_t n = (int64_t)(y1 - y0) * p.W;
     float vmax = -INFINITY, vmin = INFINITY;
@@ -181,6 +181,36 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// camera pivot per (pair, band, column tile): mid-range of the in-image pixels of the tile's footprint (its columns plus
+// the window halo, the band's rows plus halo).  One warp per tile.
+__global__ void __launch_bounds__(256)
+    camera_tile_pivot_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, float *__restrict__ campiv) {
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
+    if (tile >= ntiles) return;
+    const int lane = threadIdx.x & 31;
+    const int wt = (int)(tile % L.n_wtiles), nb = (int)((tile / L.n_wtiles) % L.NB), b = (int)(tile / ((int64_t)L.n_wtiles * L.NB));
+    const float *plane = cam + (int64_t)b * p.H * p.W;
+    const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RBH - L.r);
+    const int x0 = max(0, wt * L.WTC - L.r), x1 = min(p.W, wt * L.WTC - L.r + L.WTC + L.K - 1);
+    const int cols = x1 - x0, n = (y1 - y0) * cols;
+    float vmax = -INFINITY, vmin = INFINITY;
+    for (int e = lane; e < n; e += 32) {
+        const float v = __ldg(plane + (int64_t)(y0 + e / cols) * p.W + x0 + e % cols);
+        vmax = fmaxf(vmax, v);
+        vmin = fminf(vmin, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    }
+    if (lane == 0) {
+        const float pv = 0.5f * (vmax + vmin);
+        campiv[tile] = (vmax >= vmin && isfinite(pv)) ? pv : 0.f;
+    }
+}
+
 __device__ __forceinline__ float band_pivot(const uint32_t *__restrict__ minmax, const Problem &p,
                                             const SlidingLayout &L, int img, int b, int nb) {
     const uint32_t *mm = minmax + ((size_t)(img * p.B + b) * L.NB + nb) * 2;
@@ -193,12 +223,13 @@ __device__ __forceinline__ float band_pivot(const uint32_t *__restrict__ minmax,
 // four consecutive elements of the two band copies per thread
 __global__ void __launch_bounds__(256)
     band_copy_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
-                     const uint32_t *__restrict__ minmax, float *__restrict__ camP, float *__restrict__ projP) {
+                     const uint32_t *__restrict__ minmax, const float *__restrict__ campiv,
+                     float *__restrict__ camP, float *__restrict__ projP) {
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B;
-    const int pitch = img ? L.proj_pitch : L.cam_pitch, left = img ? L.proj_lp : L.cam_lc;
+    const int pitch = img ? L.proj_pitch : L.cam_pitch, left = L.proj_lp;
     const int t = blockIdx.y % L.RBH, nb = blockIdx.y / L.RBH;
     const int y = nb * L.RB - L.r + t;
-    const float pv = band_pivot(minmax, p, L, img, b, nb);
+    const float pvb = img ? band_pivot(minmax, p, L, 1, b, nb) : 0.f;
     const float *row = (img ? proj : cam) + ((int64_t)b * p.H + y) * p.W;
     float *out = (img ? projP : camP) + (((int64_t)b * L.NB + nb) * L.RBH + t) * pitch;
     const bool yin = y >= 0 && y < p.H;
@@ -206,8 +237,13 @@ __global__ void __launch_bounds__(256)
     if (ci < pitch) {
         float v[4];
 #pragma unroll
+        // projector: column X sits at index X + proj_lp, one pivot per band; camera: tile-major (tile wt holds image
+        // columns wt*WTC - r + j at index wt*seg_cam + j), one pivot per tile (4 consecutive indices share a tile)
+        const int wt = img ? 0 : ci / L.seg_cam;
+        const float pv = img ? pvb : campiv[((int64_t)b * L.NB + nb) * L.n_wtiles + wt];
+        const int xbase = img ? ci - left : wt * L.WTC - L.r + (ci - wt * L.seg_cam);
         for (int e = 0; e < 4; ++e) {
-            const int x = ci + e - left;
+            const int x = xbase + e;
             v[e] = ((yin && x >= 0 && x < p.W) ? __ldg(row + x) : 0.f) - pv;
         }
         *reinterpret_cast<float4 *>(out + ci) = make_float4(v[0], v[1], v[2], v[3]);
@@ -235,11 +271,15 @@ __global__ void __launch_bounds__(128)
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y / nseg, seg = blockIdx.y % nseg;
     const int t_begin = seg * kStatRows, t_end = min(L.RBH, t_begin + kStatRows + K - 1);
     const int pitch = img ? L.ps_pitch : L.cs_pitch, left = img ? L.ps_ld : 0;
-    const int pitchP = img ? L.proj_pitch : L.cam_pitch, leftP = img ? L.proj_lp : L.cam_lc;
+    const int pitchP = img ? L.proj_pitch : L.cam_pitch;
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = ci - left;
     const bool col_ok = ci < pitch && x >= 0 && x < p.W;
-    const int c0 = col_ok ? x - L.r + leftP : 0;   // column of the copy that holds image column x - r
+    // column of the copy that holds image column x - r (camera copies are tile-major), and how far the copy extends
+    // to either side of the window (the camera's ends with its tile)
+    const int wt = x / L.WTC, xin = x - wt * L.WTC;
+    const int c0 = !col_ok ? 0 : img ? x - L.r + L.proj_lp : wt * L.seg_cam + xin;
+    const int room_l = img ? 3 : min(3, xin), room_r = img ? 3 : min(3, L.seg_cam - (xin + K));
     const float *src = (img ? projP : camP) + ((int64_t)b * L.NB + nb) * L.RBH * pitchP + c0;
     float *o1 = (img ? Sp : A) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     float *o2 = (img ? ey2 : ex2) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
@@ -264,8 +304,8 @@ __global__ void __launch_bounds__(128)
             // (tiles that can see the zero padding do not slide): take the magnitude over that span
 #pragma unroll
             for (int j = 1; j <= 3; ++j) {
-                if (x - L.r - j >= 0) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP - j]));
-                if (x - L.r + K - 1 + j < p.W) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
+                if (j <= room_l && x - L.r - j >= 0) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP - j]));
+                if (j <= room_r && x - L.r + K - 1 + j < p.W) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
             }
         }
         float s1 = h1, s2 = h2, sm = hm;
@@ -285,11 +325,14 @@ __global__ void __launch_bounds__(128)
             if (ok && sm > 0.f) rho = fmaxf(rho, (float)(K * K) * sm * sm / e2);   // e2 == 0 -> inf
         }
     }
+    // non-negative floats (and +inf) order like unsigned integers
+    if (img) {   // projector: worst window per block of 16 statistics columns
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
-    if ((threadIdx.x & 15) == 0 && ci < pitch) {
-        float *mx = (img ? rho_p : rho_c) + ((int64_t)b * L.NB + nb) * (img ? L.nblk_ps : L.nblk_cs) + ci / 16;
-        atomicMax(reinterpret_cast<uint32_t *>(mx), __float_as_uint(rho));   // non-negative floats (and +inf) order like uints
+        for (int o = 8; o > 0; o >>= 1) rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
+        if ((threadIdx.x & 15) == 0 && ci < pitch)
+            atomicMax(reinterpret_cast<uint32_t *>(rho_p + ((int64_t)b * L.NB + nb) * L.nblk_ps + ci / 16), __float_as_uint(rho));
+    } else if (col_ok && rho > 0.f) {   // camera: worst window per column tile
+        atomicMax(reinterpret_cast<uint32_t *>(rho_c + ((int64_t)b * L.NB + nb) * L.n_wtiles + wt), __float_as_uint(rho));
     }
 }
 
@@ -311,7 +354,7 @@ __global__ void __launch_bounds__(128)
     const int64_t band = (int64_t)b * L.NB + nb;
     const int w_base = wt * L.WTC;
     auto range_max = [](const float *a, int lo, int hi) { float m = 0.f; for (int i = lo / 16; i <= (hi - 1) / 16; ++i) m = fmaxf(m, a[i]); return m; };
-    const float rc = range_max(rho_c + band * L.nblk_cs, w_base, w_base + L.WTC);
+    const float rc = rho_c[band * L.n_wtiles + wt];
     uint8_t any = 0;
     for (int ch = 0; ch < L.n_chunks; ++ch) {
         const int s_base = chunk_s_base(L, p.W, w_base, ch);
@@ -328,18 +371,21 @@ __global__ void __launch_bounds__(128)
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
                         cudaStream_t stream) {
     uint32_t *minmax = (uint32_t *)(ws + L.off_minmax);
-    float *camP = (float *)(ws + L.off_camP), *projP = (float *)(ws + L.off_projP);
+    float *camP = (float *)(ws + L.off_camP), *projP = (float *)(ws + L.off_projP), *campiv = (float *)(ws + L.off_campiv);
     float *rho_c = (float *)(ws + L.off_rho_c), *rho_p = (float *)(ws + L.off_rho_p);
     CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.off_minmax, 0, L.zero_end - L.off_minmax, stream));
     {
         const int64_t n = (int64_t)L.RBH * p.W;
-        dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, 2 * p.B);
-        band_minmax_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax);
+        dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, p.B);
+        band_minmax_kernel<<<grid, 256, 0, stream>>>(p, L, proj, minmax);
         CUSTMA_LAUNCH_CHECK("band_minmax_kernel");
+        const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
+        camera_tile_pivot_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, stream>>>(p, L, cam, campiv);
+        CUSTMA_LAUNCH_CHECK("camera_tile_pivot_kernel");
     }
     {
         dim3 grid((std::max(L.cam_pitch, L.proj_pitch) / 4 + 255) / 256, L.NB * L.RBH, 2 * p.B);
-        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, camP, projP);
+        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, campiv, camP, projP);
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
