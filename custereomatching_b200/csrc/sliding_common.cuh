@@ -16,6 +16,7 @@
 
 namespace custma {
 
+constexpr int kFallbackRows = 4;    // rows of a flagged tile per fallback work item (few tiles -> cut finely)
 constexpr int kSlidingStages = 8;   // row slots of the shared-memory ring
 constexpr int kLookahead = kSlidingStages - 2;  // a slot is refilled two steps after every warp released it
 
@@ -53,6 +54,8 @@ struct SlidingLayout {
     size_t off_rho_c, off_rho_p, off_bandany, off_flags, off_tileany, zero_end;
     size_t off_campiv;              // camera pivot per (pair, band, column tile)
     size_t off_fb_pm, off_fb_ey2;   // per-pixel projector window mean / second moment for the fallback kernels
+    size_t off_fb_count, off_fb_list;   // work list of the fallback kernels: (tile, group of kFallbackRows rows) items
+    int32_t fb_groups;              // row groups per band
 };
 
 // flags[tile] != 0: the tile is ill-conditioned for the O(1) window sums and is computed by the direct kernels

@@ -11,6 +11,8 @@
 namespace custma {
 
 constexpr int kFbWarps = 8;
+constexpr int kFbRows = kFallbackRows;
+constexpr int kFbGrid = 148 * 8;   // CTAs looping over the work list (they return at once when it is empty)
 
 // chunk of the sliding tiling that owns cell (w, c) of column tile w_base
 __device__ __forceinline__ int cell_chunk(const Problem &p, const SlidingLayout &L, int w_base, int w, int c) {
@@ -49,24 +51,26 @@ __global__ void __launch_bounds__(256)
     fallback_proj_stats_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ proj,
                                const uint32_t *__restrict__ bandany, float *__restrict__ pm_out,
                                float *__restrict__ ey2_out) {
-    const int h = blockIdx.y, b = blockIdx.z;
-    if (!bandany[b * L.NB + h / L.RB]) return;
+    const int nb = blockIdx.y, b = blockIdx.z;
+    if (!bandany[b * L.NB + nb]) return;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= p.W) return;
     const float *plane = proj + (int64_t)b * p.H * p.W;
-    float pm = 0.f;
-    for (int i = 0; i < p.k; ++i)
-        for (int j = 0; j < p.k; ++j) pm += query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r);
-    pm /= (float)(p.k * p.k);
-    float ey2 = 0.f;
-    for (int i = 0; i < p.k; ++i)
-        for (int j = 0; j < p.k; ++j) {
-            const float q = query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm;
-            ey2 = fmaf(q, q, ey2);
-        }
-    const int64_t o = ((int64_t)b * p.H + h) * p.W + d;
-    pm_out[o] = pm;
-    ey2_out[o] = ey2;
+    for (int h = nb * L.RB; h < min(p.H, (nb + 1) * L.RB); ++h) {
+        float pm = 0.f;
+        for (int i = 0; i < p.k; ++i)
+            for (int j = 0; j < p.k; ++j) pm += query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r);
+        pm /= (float)(p.k * p.k);
+        float ey2 = 0.f;
+        for (int i = 0; i < p.k; ++i)
+            for (int j = 0; j < p.k; ++j) {
+                const float q = query_ij(plane, p.H, p.W, h + i - p.r, d + j - p.r) - pm;
+                ey2 = fmaf(q, q, ey2);
+            }
+        const int64_t o = ((int64_t)b * p.H + h) * p.W + d;
+        pm_out[o] = pm;
+        ey2_out[o] = ey2;
+    }
 }
 
 // centred correlation of the camera patch with the projector window of column d (reference :56-70)
@@ -81,17 +85,20 @@ __device__ __forceinline__ float cell_exy(const Problem &p, const float *proj_pl
 __global__ void __launch_bounds__(kFbWarps * 32)
     fallback_forward_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ cam,
                             const float *__restrict__ proj, const uint8_t *__restrict__ flags,
-                            const uint8_t *__restrict__ tileany, const float *__restrict__ fb_pm,
-                            const float *__restrict__ fb_ey2, float *__restrict__ cost,
-                            unsigned long long *__restrict__ keys) {
+                            const uint32_t *__restrict__ fb_count, const uint32_t *__restrict__ fb_list,
+                            const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
+                            float *__restrict__ cost, unsigned long long *__restrict__ keys) {
     extern __shared__ float smem[];
-    const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
-    const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + wt;
-    if (!tileany[t3]) return;
+    const uint32_t n_items = *fb_count;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t code = fb_list[item];
+    const int64_t t3 = code / L.fb_groups;
+    const int rg = (int)(code % L.fb_groups);
+    const int wt = (int)(t3 % L.n_wtiles), nb = (int)((t3 / L.n_wtiles) % L.NB), b = (int)(t3 / ((int64_t)L.n_wtiles * L.NB));
     const uint8_t *fl = flags + t3 * L.n_chunks;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h0 = nb * L.RB, w_base = wt * L.WTC;
-    const int rows = min(L.RB, p.H - h0), cols = min(L.WTC, p.W - w_base);
+    const int h0 = nb * L.RB + rg * kFbRows, w_base = wt * L.WTC;
+    const int rows = min(min(kFbRows, L.RB - rg * kFbRows), p.H - h0), cols = min(L.WTC, p.W - w_base);
     const float *cam_plane = cam + (int64_t)b * p.H * p.W, *proj_plane = proj + (int64_t)b * p.H * p.W;
     float *camc = smem + warp * p.k * p.k;
     for (int pi = warp; pi < rows * cols; pi += kFbWarps) {
@@ -125,23 +132,27 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                 atomicMax(keys + pix, ((unsigned long long)float_to_ordered(bv) << 32) | (uint32_t)(bs + p.W));
         }
     }
+    }   // work items
 }
 
 // patch gradient (k*k values per pixel) of the flagged cells; layout and formula of direct_patch_grad_kernel
 __global__ void __launch_bounds__(kFbWarps * 32)
     fallback_patch_grad_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ grad,
                                const float *__restrict__ cam, const float *__restrict__ proj,
-                               const uint8_t *__restrict__ flags, const uint8_t *__restrict__ tileany,
-                               const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
-                               float *__restrict__ patch_grad) {
+                               const uint8_t *__restrict__ flags, const uint32_t *__restrict__ fb_count,
+                               const uint32_t *__restrict__ fb_list, const float *__restrict__ fb_pm,
+                               const float *__restrict__ fb_ey2, float *__restrict__ patch_grad) {
     extern __shared__ float smem[];
-    const int wt = blockIdx.x, nb = blockIdx.y, b = blockIdx.z;
-    const int64_t t3 = ((int64_t)b * L.NB + nb) * L.n_wtiles + wt;
-    if (!tileany[t3]) return;
+    const uint32_t n_items = *fb_count;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t code = fb_list[item];
+    const int64_t t3 = code / L.fb_groups;
+    const int rg = (int)(code % L.fb_groups);
+    const int wt = (int)(t3 % L.n_wtiles), nb = (int)((t3 / L.n_wtiles) % L.NB), b = (int)(t3 / ((int64_t)L.n_wtiles * L.NB));
     const uint8_t *fl = flags + t3 * L.n_chunks;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kk = p.k * p.k;
-    const int h0 = nb * L.RB, w_base = wt * L.WTC;
-    const int rows = min(L.RB, p.H - h0), cols = min(L.WTC, p.W - w_base);
+    const int h0 = nb * L.RB + rg * kFbRows, w_base = wt * L.WTC;
+    const int rows = min(min(kFbRows, L.RB - rg * kFbRows), p.H - h0), cols = min(L.WTC, p.W - w_base);
     const float *cam_plane = cam + (int64_t)b * p.H * p.W, *proj_plane = proj + (int64_t)b * p.H * p.W;
     float *camc = smem + (size_t)warp * (kk + 2 * p.C);
     float *a_s = camc + kk, *pm_s = a_s + p.C;
@@ -187,11 +198,12 @@ __global__ void __launch_bounds__(kFbWarps * 32)
             if (lane == 0) patch_grad[pix * kk + t] = acc - bsum * camc[t];
         }
     }
+    }   // work items
 }
 
 static int launch_fallback_proj_stats(const Problem &p, const SlidingLayout &L, const float *proj, const char *ws,
                                       cudaStream_t stream) {
-    dim3 grid((p.W + 255) / 256, p.H, p.B);
+    dim3 grid((p.W + 255) / 256, L.NB, p.B);
     fallback_proj_stats_kernel<<<grid, 256, 0, stream>>>(p, L, proj, (const uint32_t *)(ws + L.off_bandany),
                                                          (float *)(const_cast<char *>(ws) + L.off_fb_pm),
                                                          (float *)(const_cast<char *>(ws) + L.off_fb_ey2));
@@ -203,11 +215,11 @@ int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const floa
                             const char *ws, float *cost, unsigned long long *keys, cudaStream_t stream) {
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
-    dim3 grid(L.n_wtiles, L.NB, p.B);
     const size_t smem = (size_t)kFbWarps * p.k * p.k * sizeof(float);
-    fallback_forward_kernel<<<grid, kFbWarps * 32, smem, stream>>>(
-        p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany),
-        (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost, keys);
+    fallback_forward_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
+        p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
+        (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost,
+        keys);
     CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
     return CUSTMA_OK;
 }
@@ -216,7 +228,6 @@ size_t fallback_backward_smem(const Problem &p) { return (size_t)kFbWarps * (p.k
 
 int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
                                const float *proj, const char *ws, float *patch_grad, cudaStream_t stream) {
-    dim3 grid(L.n_wtiles, L.NB, p.B);
     const size_t smem = fallback_backward_smem(p);
     if (smem > 200 * 1024)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback backward: last axis %d too long for shared memory", p.C);
@@ -224,9 +235,10 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
                                            (int)std::max<size_t>(smem, 48 * 1024)));
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
-    fallback_patch_grad_kernel<<<grid, kFbWarps * 32, smem, stream>>>(
-        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint8_t *)(ws + L.off_tileany),
-        (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), patch_grad);
+    fallback_patch_grad_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
+        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
+        (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2),
+        patch_grad);
     CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");
     return CUSTMA_OK;
 }

@@ -89,6 +89,7 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->off_rho_c = take(bands * L->n_wtiles * sizeof(float));          // per column tile
     L->off_rho_p = take(bands * L->nblk_ps * sizeof(float));
     L->off_bandany = take(bands * sizeof(uint32_t));                    // does the band hold a flagged tile?
+    L->off_fb_count = take(sizeof(uint32_t));                          // number of fallback work items
     L->zero_end = off;
     L->off_flags = take((size_t)p.B * L->NB * L->n_wtiles * L->n_chunks);
     L->off_tileany = take((size_t)p.B * L->NB * L->n_wtiles);
@@ -99,6 +100,8 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     L->off_ex2 = take(rows * L->cs_pitch * sizeof(float));
     L->off_Sp = take(rows * L->ps_pitch * sizeof(float));
     L->off_ey2 = take(rows * L->ps_pitch * sizeof(float));
+    L->fb_groups = (L->RB + kFallbackRows - 1) / kFallbackRows;
+    L->off_fb_list = take((size_t)p.B * L->NB * L->n_wtiles * L->fb_groups * sizeof(uint32_t));
     L->off_fb_pm = take((size_t)p.pixels() * sizeof(float));
     L->off_fb_ey2 = take((size_t)p.pixels() * sizeof(float));
     L->off_extra = off;
@@ -142,8 +145,8 @@ int validate_sliding_layout(const Problem &p, bool backward) {
     }
     // the column of the copies that holds image column X = -r .. W-1+(K-1-r) of every statistics window exists
     if (L.proj_lp < L.r) return bad("left apron", 0, 0, L.proj_lp, L.r);
-    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.off_bandany, L.zero_end, L.off_flags, L.off_tileany, L.off_campiv, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
-                           L.off_ey2, L.off_fb_pm, L.off_fb_ey2, L.off_extra, L.total};
+    const size_t offs[] = {L.off_minmax, L.off_wta, L.off_rho_c, L.off_rho_p, L.off_bandany, L.off_fb_count, L.zero_end, L.off_flags, L.off_tileany, L.off_campiv, L.off_camP, L.off_projP, L.off_A, L.off_ex2, L.off_Sp,
+                           L.off_ey2, L.off_fb_list, L.off_fb_pm, L.off_fb_ey2, L.off_extra, L.total};
     for (size_t i = 1; i < sizeof(offs) / sizeof(offs[0]); ++i)
         if (offs[i] < offs[i - 1] || (offs[i] & 255)) return bad("workspace offsets", (int)i, 0, (int)(offs[i] >> 8), (int)(offs[i - 1] >> 8));
     return CUSTMA_OK;
@@ -346,7 +349,8 @@ constexpr float kMaxConditioning = 40.f;
 
 __global__ void __launch_bounds__(128)
     tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ rho_c, const float *__restrict__ rho_p,
-                      uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany, uint32_t *__restrict__ bandany) {
+                      uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany, uint32_t *__restrict__ bandany,
+                      uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
     if (id >= ntiles) return;
@@ -365,7 +369,11 @@ __global__ void __launch_bounds__(128)
         any |= fast ? 0 : 1;
     }
     tileany[id] = any;
-    if (any) atomicOr(bandany + band, 1u);
+    if (any) {   // queue the tile for the fallback kernels, kFallbackRows rows per work item
+        atomicOr(bandany + band, 1u);
+        const uint32_t first = atomicAdd(fb_count, (uint32_t)L.fb_groups);
+        for (int g = 0; g < L.fb_groups; ++g) fb_list[first + g] = (uint32_t)(id * L.fb_groups + g);
+    }
 }
 
 int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj, char *ws,
@@ -399,7 +407,7 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
         const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
         tile_flags_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, stream>>>(
             p, L, rho_c, rho_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany),
-            (uint32_t *)(ws + L.off_bandany));
+            (uint32_t *)(ws + L.off_bandany), (uint32_t *)(ws + L.off_fb_count), (uint32_t *)(ws + L.off_fb_list));
         CUSTMA_LAUNCH_CHECK("tile_flags_kernel");
     }
     return CUSTMA_OK;
