@@ -196,13 +196,13 @@ __global__ void __launch_bounds__(256)
     const float *plane = cam + (int64_t)b * p.H * p.W;
     const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RBH - L.r);
     const int x0 = max(0, wt * L.WTC - L.r), x1 = min(p.W, wt * L.WTC - L.r + L.WTC + L.K - 1);
-    const int cols = x1 - x0, n = (y1 - y0) * cols;
     float vmax = -INFINITY, vmin = INFINITY;
-    for (int e = lane; e < n; e += 32) {
-        const float v = __ldg(plane + (int64_t)(y0 + e / cols) * p.W + x0 + e % cols);
-        vmax = fmaxf(vmax, v);
-        vmin = fminf(vmin, v);
-    }
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const float v = __ldg(plane + (int64_t)y * p.W + x);
+            vmax = fmaxf(vmax, v);
+            vmin = fminf(vmin, v);
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
