@@ -1,13 +1,12 @@
 // Shared pieces of the sliding-window kernels (sliding_prep.cu, sliding_forward.cu, sliding_backward.cu):
-// the tiling, the workspace layout the prep kernels fill and the main kernels stream through TMA bulk copies,
-// and the mbarrier / cp.async.bulk PTX wrappers (sm_100a).
+// the tiling, the workspace layout the prep kernels fill and the main kernels stream into shared memory with
+// cp.async + mbarrier, and the PTX wrappers for those (sm_100a).
 //
 // Tiling of the cost volume (reference: custma/src/stereo_matching_kernel.cu:17-72 computes one cell per thread):
 //   thread        4 camera columns x 4 disparities, marching down the rows of a row band; the k x k window sum of
-//                 the product image cam[y,x] * proj[y,x-s] is kept as a register ring of k-1 horizontal sums
+//                 the product image cam[y,x] * proj[y,x-s] is kept as a register ring of k-1 row sums (BoxRing)
 //   unit          16 lanes = 64 consecutive disparities of the same 4 columns (lane l owns s0 = s_base+64*su+4*l)
-//   CTA           NU units x WG column groups (+1 producer warp) = a tile of WTC = 4*WG columns, SC = 64*NU
-//                 disparities, RB rows
+//   CTA           NU units x WG column groups = a tile of WTC = 4*WG columns, SC = 64*NU disparities, RB rows
 // With the last axis of the volume on the lanes every store is a run of >= 256 contiguous bytes.
 // s is the disparity (projector column d = w - s).  In banded mode s runs over [0, D); in full (reference-shaped)
 // mode the same kernel covers s in [w - (W-1), w], i.e. every projector column, and writes cell [h, w, d = w - s].
@@ -39,7 +38,7 @@ struct SlidingLayout {
     int32_t K, r, NU, WG, WTC, SC;
     int32_t RB, RBH, NB;          // rows per band, rows of a band copy (RB + K - 1), number of bands
     int32_t n_wtiles, n_chunks;   // column tiles, disparity chunks per column tile
-    int32_t banded, smin_full;    // full mode: chunk c of tile wt starts at rounddown4(w_base - (W-1)) + c*SC
+    int32_t banded, smin_full;    // full mode: chunk c of tile wt starts at rounddown4(w_base - (W-1)) + c*SC (chunk_s_base)
     int32_t cam_lc, cam_pitch;    // pivoted camera copy: [B][NB][RBH][cam_pitch], tile-major: tile wt holds image
                                   // columns wt*WTC - r + j at index wt*seg_cam + j (j < seg_cam), shifted by the
                                   // tile's own pivot; cam_lc is unused (kept 0)

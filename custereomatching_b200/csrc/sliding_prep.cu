@@ -1,16 +1,19 @@
 // Prep kernels of the sliding-window path: they turn the two images into the aligned, padded, pivoted arrays that
-// the main kernels stream through TMA bulk copies with no bounds checks and no per-element address arithmetic.
+// the main kernels stream into shared memory with no bounds checks and no per-element address arithmetic, and they
+// decide per tile whether the fast kernels may be used at all.
 //
-//   band_minmax_kernel   per (image, pair, row band): min / max of the in-image pixels -> pivot = mid-range.
-//                        ZNCC is invariant to a constant added to an image (reference kernel.cu:39-70 subtracts the
-//                        window mean); subtracting a band-local constant first keeps the raw products small, which is
-//                        what makes the O(1)-per-cell window sums safe in fp32.
-//   band_copy_kernel     pivoted copies with aprons: out-of-image pixels hold (0 - pivot), i.e. the reference's zero
-//                        padding (query_ij, kernel.cu:6-12) in pivoted coordinates.
-//   band_stats_kernel    per pixel: window sum and centred second moment (one pass, sum v^2 - (sum v)^2 / n) of the
-//                        PIVOTED values.  Statistics are taken from the shifted data so that
-//                        exy = sum(cam'*proj') - A*Sp cancels consistently.
-//   tile_flags_kernel    per tile: can the fp32 error of the raw window sums exceed the tolerance?  (-> fallback)
+//   band_minmax_kernel        projector: min / max of the in-image pixels of every row band -> pivot = mid-range
+//   camera_tile_pivot_kernel  camera: the same per (band, column tile), over the tile's columns + window halo.
+//                             ZNCC is invariant to a constant added to an image (reference kernel.cu:39-70 subtracts
+//                             the window mean); subtracting a local constant first keeps the raw products small,
+//                             which is what makes the O(1)-per-cell window sums safe in fp32.
+//   band_copy_kernel          pivoted copies: out-of-image pixels hold (0 - pivot), i.e. the reference's zero padding
+//                             (query_ij, kernel.cu:6-12) in pivoted coordinates; projector rows carry aprons so that
+//                             every tile's segment is a 16-byte aligned run, camera rows are stored tile-major
+//   band_stats_kernel         per pixel: window sum / mean and centred second moment of the PIVOTED values (so that
+//                             exy = sum(cam'*proj') - A*Sp cancels consistently), and the conditioning rho of the window
+//   tile_flags_kernel         per tile: can the fp32 error of the raw window sums exceed the tolerance?  Flagged tiles
+//                             are queued for the direct-arithmetic fallback kernels (sliding_fallback.cu).
 #include <algorithm>
 
 #include "sliding_common.cuh"
