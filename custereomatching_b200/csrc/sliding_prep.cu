@@ -242,12 +242,12 @@ __global__ void __launch_bounds__(256)
     const int ci = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (ci < pitch) {
         float v[4];
-#pragma unroll
         // projector: column X sits at index X + proj_lp, one pivot per band; camera: tile-major (tile wt holds image
         // columns wt*WTC - r + j at index wt*seg_cam + j), one pivot per tile (4 consecutive indices share a tile)
         const int wt = img ? 0 : ci / L.seg_cam;
         const float pv = img ? pvb : campiv[((int64_t)b * L.NB + nb) * L.n_wtiles + wt];
         const int xbase = img ? ci - left : wt * L.WTC - L.r + (ci - wt * L.seg_cam);
+#pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int x = xbase + e;
             v[e] = ((yin && x >= 0 && x < p.W) ? __ldg(row + x) : 0.f) - pv;
