@@ -432,3 +432,37 @@ def test_image_families_keep_parity(kind):
     truth = zo.camera_grad_banded_autograd(cam, proj, gb, D, k).numpy()
     grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D)
     assert_grad_close_or_nearer_truth(grad.cpu().numpy(), gref, truth)
+
+
+def test_fuzz_fast_path_against_direct_path():
+    """Random shapes (batch, odd sizes, every fast-path window size, banded and reference-shaped): the sliding-window
+    kernels against the direct two-pass kernels (which are themselves pinned to the reference), same tolerances."""
+    rng = np.random.RandomState(2026)
+    for case in range(48):
+        k = int(rng.choice([3, 5, 5, 5, 7]))
+        B = int(rng.choice([1, 1, 2, 3]))
+        H = int(rng.randint(1, 140))
+        W = int(rng.randint(1, 330))
+        D = int(rng.choice([0, 1, 4, 17, 32, 64, 100, 128, 192, 200, 256]))
+        if D == 0 and W > 200:
+            W = 200                                    # keep the [H,W,W] volumes small
+        shape = (B, H, W) if B > 1 else (H, W)
+        pedestal, contrast = float(rng.choice([0.0, 0.3])), float(rng.choice([1.0, 0.4]))
+        cam = dev((pedestal + contrast * rng.rand(*shape)).astype(np.float32))
+        proj = dev((pedestal + contrast * rng.rand(*shape)).astype(np.float32))
+        tag = f"case {case}: B={B} H={H} W={W} D={D} k={k} pedestal={pedestal} contrast={contrast}"
+        c0, b0, i0 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True, flags=cb.FLAG_DIRECT)
+        c1, b1, i1 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True)
+        assert_cost_close(c1.cpu().numpy(), c0.cpu().numpy(), what=tag + " cost")
+        # the fused WTA is the arg-max of the kernel's own volume (ties to the lowest projector column)
+        if D > 0:
+            tb, ti = torch.flip(c1, dims=[-1]).max(dim=-1)
+            assert torch.equal(b1, tb) and torch.equal(i1.long(), (D - 1) - ti), tag + " wta"
+        else:
+            tb, ti = c1.max(dim=-1)
+            assert torch.equal(b1, tb) and torch.equal(i1.long(), ti), tag + " wta"
+        C = D if D > 0 else W
+        g = torch.from_numpy(rng.randn(*(shape + (C,))).astype(np.float32)).cuda()
+        g0 = cb.backward(g, cam, proj, k, D, flags=cb.FLAG_DIRECT)
+        g1 = cb.backward(g, cam, proj, k, D)
+        assert_grad_close(g1.cpu().numpy(), g0.cpu().numpy(), what=tag + " grad", tol=2e-5)
