@@ -78,5 +78,42 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     return LIB_PATH
 
 
+def torch_module_path() -> str:
+    import sysconfig
+    return os.path.join(ROOT, "custma", "src" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_torch_module(force: bool = False, verbose: bool = False) -> str:
+    """Builds custma/src.<abi>.so - the reference's native module name (setup.py:30-38 builds `custma.src`) - from
+    csrc/torch_binding.cpp with g++ against the installed torch, linked to libcustma_b200.so.  No CUDA code here."""
+    import sysconfig
+    out = torch_module_path()
+    src = os.path.join(CSRC, "torch_binding.cpp")
+    hdr = os.path.join(INCLUDE, "custma_b200.h")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return out
+    build()   # libcustma_b200.so first
+    import torch
+    from torch.utils import cpp_extension as ce
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+           "-DTORCH_EXTENSION_NAME=src", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI))]
+    cmd += [f"-I{i}" for i in ce.include_paths()] + ["-I/usr/local/cuda/include", f"-I{sysconfig.get_paths()['include']}",
+                                                     f"-I{INCLUDE}"]
+    cmd += [src, "-o", out + ".tmp", f"-L{PKG_DIR}", "-lcustma_b200", f"-L{torch_lib}", "-lc10", "-lc10_cuda",
+            "-ltorch_cpu", "-ltorch", "-ltorch_python",
+            "-Wl,-rpath,$ORIGIN/../custereomatching_b200", f"-Wl,-rpath,{torch_lib}"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout, file=sys.stderr, flush=True)
+        raise RuntimeError("building custma.src failed")
+    os.replace(out + ".tmp", out)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_module(force="--force" in sys.argv, verbose="-v" in sys.argv))

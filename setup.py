@@ -38,8 +38,9 @@ class build_ext(Command):
         pass
 
     def run(self):
-        from custereomatching_b200.build import build
+        from custereomatching_b200.build import build, build_torch_module
         print(build(force=bool(self.force), verbose=True))
+        print(build_torch_module(force=bool(self.force), verbose=True))   # custma/src.<abi>.so, the reference's module name
 
 
 class build_py_with_lib(build_py):
@@ -53,7 +54,7 @@ setup(
     version=get_version(),
     description="B200-native ZNCC stereo-matching cost volume (drop-in for lzhnb/CuStereoMatching's custma)",
     packages=["custma", "custereomatching_b200"],
-    package_data={"custereomatching_b200": ["libcustma_b200.so", "csrc/*"]},
+    package_data={"custereomatching_b200": ["libcustma_b200.so", "csrc/*"], "custma": ["src.*.so"]},
     cmdclass={"build_ext": build_ext, "build_py": build_py_with_lib},
     zip_safe=False,
 )

@@ -14,6 +14,10 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the native pieces are built in-tree (nvcc / g++ cross-compile without a GPU); nothing falls back to Python
+    from custereomatching_b200 import build as _build
+    _build.build()
+    _build.build_torch_module()
 
 
 def pytest_collection_modifyitems(config, items):
