@@ -15,6 +15,7 @@
 //   tile_flags_kernel         per tile: can the fp32 error of the raw window sums exceed the tolerance?  Flagged tiles
 //                             are queued for the direct-arithmetic fallback kernels (sliding_fallback.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "sliding_common.cuh"
 
