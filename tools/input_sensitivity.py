@@ -32,6 +32,30 @@ cases = {
     "ramp + texture std 0.015 (low texture)": (ramp + 0.05 * (rnd() - 0.5), ramp + 0.05 * (proj - 0.5)),
     "flat 0.8 + 0.2% noise (no texture)": (0.8 + 0.002 * rnd(), 0.8 + 0.002 * proj),
 }
+
+
+def pink(alpha, seed):
+    """1/f^alpha noise scaled to [0, 1]: the spectrum of natural images is close to alpha = 1"""
+    gg = torch.Generator(device="cuda").manual_seed(seed)
+    spec = torch.fft.rfft2(torch.randn(H, W + D, device="cuda", generator=gg))
+    fy = torch.fft.fftfreq(H, device="cuda")[:, None]
+    fx = torch.fft.rfftfreq(W + D, device="cuda")[None, :]
+    f = torch.sqrt(fx * fx + fy * fy)
+    f[0, 0] = 1.0
+    img = torch.fft.irfft2(spec / f ** alpha, s=(H, W + D))
+    img = (img - img.min()) / (img.max() - img.min())
+    return img
+
+
+for alpha in (1.0, 1.5, 2.0):
+    scene = pink(alpha, 3)
+    # a rectified pair of the same scene: constant disparity 40 plus 1 % sensor noise in each view
+    left = (scene[:, D - 40:D - 40 + W] + 0.01 * torch.randn(H, W, device="cuda", generator=g)).contiguous()
+    right = (scene[:, D:D + W] + 0.01 * torch.randn(H, W, device="cuda", generator=g)).contiguous()
+    cases[f"natural-like pair: 1/f^{alpha} scene, disparity 40, 1% noise"] = (right, left)
+blocks = torch.rand(H // 25 + 1, W // 54 + 1, device="cuda", generator=g).repeat_interleave(25, 0).repeat_interleave(54, 1)[:H, :W]
+cases["piecewise-constant blocks + 1% noise (cartoon)"] = (blocks + 0.01 * torch.randn(H, W, device="cuda", generator=g),
+                                                          blocks.roll(-20, 1) + 0.01 * torch.randn(H, W, device="cuda", generator=g))
 gin = torch.randn(H, W, D, device="cuda", generator=g)
 for name, (cam, prj) in cases.items():
     cam, prj = cam.contiguous(), prj.contiguous()
