@@ -9,8 +9,8 @@
 The drop-in Python surface of the reference lives in the top-level `custma` package.
 """
 from . import binding
-from .functional import (FLAG_DIRECT, INVALID_COST, backward, confidence_mask, cost_volume, cost_volume_and_wta,
+from .functional import (FLAG_DIRECT, FLAG_TENSOR, INVALID_COST, backward, confidence_mask, cost_volume, cost_volume_and_wta,
                          forward, wta)
 
 __all__ = ["binding", "forward", "backward", "cost_volume", "wta", "cost_volume_and_wta", "confidence_mask",
-           "FLAG_DIRECT", "INVALID_COST"]
+           "FLAG_DIRECT", "FLAG_TENSOR", "INVALID_COST"]

@@ -20,6 +20,7 @@ ERR_WORKSPACE = 2
 ERR_CUDA = 3
 ERR_UNSUPPORTED = 4
 FLAG_DIRECT = 1
+FLAG_TENSOR = 2
 INVALID_COST = -2.0
 ABI_VERSION = 1
 

@@ -65,7 +65,12 @@ bool sliding_backward_supported(const Problem &p);
 size_t sliding_forward_workspace_bytes(const Problem &p);
 size_t sliding_backward_workspace_bytes(const Problem &p);
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
-                           int32_t *index, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                           int32_t *index, void *workspace, size_t workspace_bytes, bool force_tensor,
+                           cudaStream_t stream);
+// tensor-core forward (tc_forward.cu): runs when fb_count is NULL or *fb_count > threshold, writes packed WTA keys
+bool tc_forward_supported(const Problem &p);
+int launch_tc_forward(const Problem &p, const float *cam, const float *proj, float *cost, unsigned long long *keys,
+                      const uint32_t *fb_count, uint32_t threshold, cudaStream_t stream);
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
                             float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 

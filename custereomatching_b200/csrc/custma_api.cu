@@ -122,8 +122,11 @@ int custma_forward(const float *camera, const float *projector, float *cost_volu
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
     if ((rc = carve_stats(p, workspace, workspace_bytes, forward_ws(p, flags), &s))) return rc;
+    if ((flags & CUSTMA_FLAG_TENSOR) && ((flags & CUSTMA_FLAG_DIRECT) || !tc_forward_supported(p) || !sliding_forward_supported(p)))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 572, k = 3 or 5, and no CUSTMA_FLAG_DIRECT");
     if (use_sliding_fwd(p, flags))
-        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, s.rest, s.rest_bytes, stream);
+        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, s.rest, s.rest_bytes,
+                                      (flags & CUSTMA_FLAG_TENSOR) != 0, stream);
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream);

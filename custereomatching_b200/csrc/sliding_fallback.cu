@@ -87,9 +87,10 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                             const float *__restrict__ proj, const uint8_t *__restrict__ flags,
                             const uint32_t *__restrict__ fb_count, const uint32_t *__restrict__ fb_list,
                             const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
-                            float *__restrict__ cost, unsigned long long *__restrict__ keys) {
+                            float *__restrict__ cost, unsigned long long *__restrict__ keys, const uint32_t tc_threshold) {
     extern __shared__ float smem[];
     const uint32_t n_items = *fb_count;
+    if (n_items > tc_threshold) return;   // so much is flagged that the tensor-core kernel computes the whole call
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const uint32_t code = fb_list[item];
     const int64_t t3 = code / L.fb_groups;
@@ -212,14 +213,15 @@ static int launch_fallback_proj_stats(const Problem &p, const SlidingLayout &L, 
 }
 
 int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
-                            const char *ws, float *cost, unsigned long long *keys, cudaStream_t stream) {
+                            const char *ws, float *cost, unsigned long long *keys, uint32_t tc_threshold,
+                            cudaStream_t stream) {
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
     const size_t smem = (size_t)kFbWarps * p.k * p.k * sizeof(float);
     fallback_forward_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
         p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost,
-        keys);
+        keys, tc_threshold);
     CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
     return CUSTMA_OK;
 }

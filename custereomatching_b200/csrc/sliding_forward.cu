@@ -30,7 +30,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
 template <int K, int NU, int WG, bool COST, bool WTA>
 __global__ void __launch_bounds__(16 * NU * WG, 2)
     sliding_forward_kernel(const Problem p, const SlidingLayout L, const char *__restrict__ ws,
-                           float *__restrict__ cost, unsigned long long *__restrict__ wta_keys) {
+                           float *__restrict__ cost, unsigned long long *__restrict__ wta_keys, const uint32_t tc_threshold) {
     using G = SlideGeom<K, NU, WG>;
     constexpr int WTC = G::WTC, SC = G::SC, NS = G::NS, NCW = G::NCW;
     extern __shared__ __align__(128) float smem[];
@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     const int rows = min(L.RB, p.H - h0);
     // row steps, padded to whole periods of the pair-sum ring (the band copies and statistics rows cover the padding)
     const int steps = (rows + K - 1 + G::PERIOD - 1) / G::PERIOD * G::PERIOD;
+    // so many flagged tiles that the tensor-core kernel (tc_forward.cu) computes the whole call
+    if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
     // ill-conditioned tiles belong to the direct two-pass kernels (sliding_fallback.cu)
     if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) return;
 
@@ -221,33 +223,33 @@ __global__ void __launch_bounds__(256)
 
 template <int K, int NU, int WG, bool COST, bool WTA>
 static int launch_one(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                      unsigned long long *keys, cudaStream_t stream) {
+                      unsigned long long *keys, uint32_t tc_threshold, cudaStream_t stream) {
     const size_t smem = (size_t)kSlidingStages * SlideGeom<K, NU, WG>::SLOT * sizeof(float);
     const int threads = 16 * NU * WG;
     auto kern = sliding_forward_kernel<K, NU, WG, COST, WTA>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys);
+    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys, tc_threshold);
     CUSTMA_LAUNCH_CHECK("sliding_forward_kernel");
     return CUSTMA_OK;
 }
 
 template <int K, int NU, int WG>
 static int launch_cfg(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                      unsigned long long *keys, cudaStream_t stream) {
-    if (cost && keys) return launch_one<K, NU, WG, true, true>(p, L, ws, cost, keys, stream);
-    if (cost) return launch_one<K, NU, WG, true, false>(p, L, ws, cost, keys, stream);
-    return launch_one<K, NU, WG, false, true>(p, L, ws, cost, keys, stream);
+                      unsigned long long *keys, uint32_t thr, cudaStream_t stream) {
+    if (cost && keys) return launch_one<K, NU, WG, true, true>(p, L, ws, cost, keys, thr, stream);
+    if (cost) return launch_one<K, NU, WG, true, false>(p, L, ws, cost, keys, thr, stream);
+    return launch_one<K, NU, WG, false, true>(p, L, ws, cost, keys, thr, stream);
 }
 
 template <int K>
 static int launch_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                    unsigned long long *keys, cudaStream_t stream) {
+                    unsigned long long *keys, uint32_t thr, cudaStream_t stream) {
     switch (cfg.NU) {
-        case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, stream);
-        case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, stream);
-        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, stream);
-        default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, stream);
+        case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, thr, stream);
+        case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, thr, stream);
+        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, thr, stream);
+        default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, thr, stream);
     }
 }
 
@@ -264,8 +266,14 @@ size_t sliding_forward_workspace_bytes(const Problem &p) {
     return L.total;
 }
 
+// Share of the fallback work list (flagged tiles x row groups) above which the whole call goes to the tensor-core
+// kernel: the per-cell fallback runs at ~40 Gcell/s, the tensor-core kernel at ~430, the sliding kernel at ~850, so
+// the cross-over is at about 5 % flagged.
+constexpr double kTensorShare = 0.04;
+
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
-                           int32_t *index, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                           int32_t *index, void *workspace, size_t workspace_bytes, bool force_tensor,
+                           cudaStream_t stream) {
     SlidingConfig cfg;
     if (!sliding_pick_config(p, false, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
@@ -273,14 +281,25 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
     if (workspace_bytes < L.total)
         return set_error(CUSTMA_ERR_WORKSPACE, "sliding forward needs %zu workspace bytes, %zu given", L.total, workspace_bytes);
     char *ws = (char *)workspace;
-    int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
-    if (rc) return rc;
     unsigned long long *keys = best ? (unsigned long long *)(ws + L.off_wta) : nullptr;
-    rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, stream)
-       : p.k == 5 ? launch_k<5>(cfg, p, L, ws, cost, keys, stream)
-                  : launch_k<7>(cfg, p, L, ws, cost, keys, stream);
-    if (rc) return rc;
-    if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, stream))) return rc;
+    int rc;
+    if (force_tensor) {
+        if (!tc_forward_supported(p))
+            return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 572 and k = 3 or 5");
+        if ((rc = launch_tc_forward(p, cam, proj, cost, keys, nullptr, 0, stream))) return rc;   // writes every key itself
+    } else {
+        if ((rc = launch_sliding_prep(p, L, cam, proj, ws, stream))) return rc;
+        const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;
+        const uint32_t thr = tc_forward_supported(p) ? (uint32_t)(kTensorShare * items) : 0xffffffffu;
+        rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, thr, stream)
+           : p.k == 5 ? launch_k<5>(cfg, p, L, ws, cost, keys, thr, stream)
+                      : launch_k<7>(cfg, p, L, ws, cost, keys, thr, stream);
+        if (rc) return rc;
+        if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, thr, stream))) return rc;
+        if (thr != 0xffffffffu &&
+            (rc = launch_tc_forward(p, cam, proj, cost, keys, (const uint32_t *)(ws + L.off_fb_count), thr, stream)))
+            return rc;
+    }
     if (best) {
         wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index);
         CUSTMA_LAUNCH_CHECK("wta_decode_kernel");

@@ -22,6 +22,7 @@ from . import binding
 
 INVALID_COST = binding.INVALID_COST
 FLAG_DIRECT = binding.FLAG_DIRECT
+FLAG_TENSOR = binding.FLAG_TENSOR
 
 
 def _check_input(x: torch.Tensor, name: str) -> None:

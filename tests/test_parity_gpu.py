@@ -454,6 +454,11 @@ def test_fuzz_fast_path_against_direct_path():
         c0, b0, i0 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True, flags=cb.FLAG_DIRECT)
         c1, b1, i1 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True)
         assert_cost_close(c1.cpu().numpy(), c0.cpu().numpy(), what=tag + " cost")
+        if D > 0 and D % 4 == 0 and k in (3, 5):     # the tensor-core forward on the same input
+            c2, b2, i2 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True, flags=cb.FLAG_TENSOR)
+            assert_cost_close(c2.cpu().numpy(), c0.cpu().numpy(), what=tag + " tensor-core cost")
+            tb, ti = torch.flip(c2, dims=[-1]).max(dim=-1)
+            assert torch.equal(b2, tb) and torch.equal(i2.long(), (D - 1) - ti), tag + " tensor-core wta"
         # the fused WTA is the arg-max of the kernel's own volume (ties to the lowest projector column)
         if D > 0:
             tb, ti = torch.flip(c1, dims=[-1]).max(dim=-1)
@@ -466,3 +471,77 @@ def test_fuzz_fast_path_against_direct_path():
         g0 = cb.backward(g, cam, proj, k, D, flags=cb.FLAG_DIRECT)
         g1 = cb.backward(g, cam, proj, k, D)
         assert_grad_close(g1.cpu().numpy(), g0.cpu().numpy(), what=tag + " grad", tol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core forward (tc_forward.cu): forced with FLAG_TENSOR, and picked by the verdict for low-texture inputs
+# ---------------------------------------------------------------------------------------------------------------
+TENSOR_CASES = [  # H, W, D, k  (banded, D % 4 == 0, k = 3 or 5)
+    (24, 40, 16, 5), (9, 21, 32, 5), (3, 10, 4, 5), (40, 131, 96, 5), (33, 260, 192, 5), (64, 300, 256, 5),
+    (150, 300, 64, 3), (70, 420, 192, 3), (200, 520, 192, 5), (37, 700, 100, 5), (12, 140, 572, 5), (1, 1, 4, 3),
+    (45, 128, 44, 5), (45, 129, 48, 5), (7, 257, 220, 3),
+]
+
+
+@pytest.mark.parametrize("H,W,D,k", TENSOR_CASES)
+def test_tensor_core_forward_vs_oracle(H, W, D, k):
+    cam, proj = rand_pair(H, W, seed=H * 1000 + W + 1)
+    ref = ref_port.forward_banded(cam, proj, D, k)
+    cost, best, disp = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True, flags=cb.FLAG_TENSOR)
+    cost = cost.cpu().numpy()
+    assert_cost_close(cost, ref)
+    invalid = np.arange(W)[:, None] - np.arange(D)[None, :] < 0
+    assert (cost[:, invalid] == cb.INVALID_COST).all()
+    ob, od = ref_port.wta_banded(cost)
+    assert np.array_equal(best.cpu().numpy(), ob)
+    assert np.array_equal(disp.cpu().numpy(), od)
+    rb, rd = ref_port.wta_banded(ref)
+    top = np.sort(np.where(invalid[None], -np.inf, ref), axis=-1)
+    gap = top[..., -1] - (top[..., -2] if D > 1 else -np.inf)
+    sel = gap > COST_TOL
+    assert np.array_equal(disp.cpu().numpy()[sel], rd[sel])
+    b2, d2 = cb.wta(dev(cam), dev(proj), D, k, flags=cb.FLAG_TENSOR)
+    assert torch.equal(b2, best) and torch.equal(d2, disp)
+    c3 = cb.cost_volume(dev(cam), dev(proj), D, k, flags=cb.FLAG_TENSOR)
+    assert np.array_equal(c3.cpu().numpy(), cost)
+
+
+def test_tensor_core_forward_batched_equals_per_pair():
+    B, H, W, D, k = 3, 50, 300, 128, 5
+    cam, proj = rand_pair(H, W, seed=77, B=B)
+    cost, best, disp = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True, flags=cb.FLAG_TENSOR)
+    for b in range(B):
+        c1, b1, d1 = cb.forward(dev(cam[b]), dev(proj[b]), D, k, want_cost=True, want_wta=True, flags=cb.FLAG_TENSOR)
+        assert torch.equal(cost[b], c1) and torch.equal(best[b], b1) and torch.equal(disp[b], d1)
+
+
+def test_tensor_core_flag_is_refused_where_unsupported():
+    cam, proj = rand_pair(16, 40, seed=3)
+    for D, k in ((0, 5), (6, 5), (32, 7), (576, 5)):
+        with pytest.raises(RuntimeError):
+            cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=False, flags=cb.FLAG_TENSOR)
+    with pytest.raises(RuntimeError):
+        cb.forward(dev(cam), dev(proj), 32, 5, want_cost=True, want_wta=False, flags=cb.FLAG_TENSOR | cb.FLAG_DIRECT)
+
+
+def test_verdict_hands_low_texture_inputs_to_the_tensor_core_kernel():
+    """A smooth scene with 1 % noise flags (nearly) every tile of the sliding-window path; the default call must then
+    give exactly the tensor-core kernel's bits - and stay within tolerance of the reference arithmetic.  A textured
+    input must keep running the sliding-window kernels (different bits, same tolerance)."""
+    H, W, D, k = 96, 600, 192, 5
+    rng = np.random.RandomState(5)
+    xx = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)
+    yy = np.arange(H, dtype=np.float32)[:, None].repeat(W, 1)
+    scene = lambda sh: 0.5 + 0.4 * np.sin((xx + sh) * 0.01) * np.cos(yy * 0.02)
+    cam = np.ascontiguousarray(scene(0) + 0.01 * (rng.rand(H, W) - 0.5), np.float32)
+    proj = np.ascontiguousarray(scene(40) + 0.01 * (rng.rand(H, W) - 0.5), np.float32)
+    ref = ref_port.forward_banded(cam, proj, D, k)
+    c_def, b_def, d_def = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True)
+    c_tc, b_tc, d_tc = cb.forward(dev(cam), dev(proj), D, k, want_cost=True, want_wta=True, flags=cb.FLAG_TENSOR)
+    assert torch.equal(c_def, c_tc) and torch.equal(b_def, b_tc) and torch.equal(d_def, d_tc)
+    assert_cost_close(c_def.cpu().numpy(), ref)
+    cam, proj = rand_pair(H, W, seed=9)
+    c_def = cb.cost_volume(dev(cam), dev(proj), D, k)
+    c_tc = cb.cost_volume(dev(cam), dev(proj), D, k, flags=cb.FLAG_TENSOR)
+    assert not torch.equal(c_def, c_tc)
+    assert_cost_close(c_def.cpu().numpy(), c_tc.cpu().numpy())

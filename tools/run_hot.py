@@ -18,6 +18,7 @@ ap.add_argument("--workload", default="kitti")
 ap.add_argument("--pairs", type=int, default=0)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--direct", action="store_true")
+ap.add_argument("--tensor", action="store_true", help="force the tensor-core forward")
 ap.add_argument("--no-wta", action="store_true")
 ap.add_argument("--no-cost", action="store_true")
 ap.add_argument("--full", action="store_true", help="reference-shaped [H,W,W] volume (D = 0)")
@@ -27,7 +28,7 @@ if a.full:
     D = 0
 P = a.pairs or P0
 C = D if D > 0 else W
-flags = binding.FLAG_DIRECT if a.direct else 0
+flags = binding.FLAG_DIRECT if a.direct else binding.FLAG_TENSOR if a.tensor else 0
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 g = torch.Generator().manual_seed(0)

@@ -15,7 +15,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 
-constexpr int KW = 5, R = 2, TAPS = 32, MT = 128, D = 192, NP = 320, NH = 160;
+constexpr int KW = 5, R = 2, TAPS = 32, MT = 128, D = 192, NP = 320;
 constexpr float kEps = 1e-8f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,20 +72,49 @@ __device__ __forceinline__ void build_row(const float *img, int H, int W, int y,
     }
 }
 
-__global__ void __launch_bounds__(256) tc_forward(const float *__restrict__ cam, const float *__restrict__ proj,
-                                                  float *__restrict__ out, int H, int W, int passes) {
+// v2: one CTA = 128 camera columns x a band of rows.  Per row the projector range is cut into NBLK blocks of NB columns;
+// a "job" is (row, block).  Iteration j: all warps build the operand tiles of job j in shared memory, one thread issues
+// the MMAs of job j into TMEM buffer j&1, then all warps run the epilogue of job j-1 out of buffer (j-1)&1 while the
+// tensor core works.  The epilogue thread owns one camera column (TMEM lane), so the WTA is a thread-local running
+// maximum; costs are transposed through a per-warp shared-memory stage and written as contiguous runs.
+constexpr int NB = 160, NBLK = NP / NB, HALF = NB / 2, STAGE_LD = HALF + 4;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+#define TMEM_LD16(r, taddr)                                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                       \
+                 : "r"(taddr))
+
+__global__ void __launch_bounds__(256, 1) tc_forward(const float *__restrict__ cam, const float *__restrict__ proj,
+                                                     float *__restrict__ out, float *__restrict__ best, int *__restrict__ index,
+                                                     int H, int W, int RB, int passes, long long *dbg) {
+    long long t_wait = 0, t_build = 0, t_mma = 0, t_math = 0, t_out = 0, t_sync = 0, tc;
+#define TICK() tc = clock64()
+#define TOCK(acc) acc += clock64() - tc
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *Ahi = reinterpret_cast<float *>(smem_raw);          // [8][128][4]
     float *Alo = Ahi + MT * TAPS;
-    float *Bhi = Alo + MT * TAPS;                               // [8][320][4]
-    float *Blo = Bhi + NP * TAPS;
-    float *ex2 = Blo + NP * TAPS;                               // [128]
-    float *ey2 = ex2 + MT;                                      // [320]
-    __shared__ __align__(8) unsigned long long mbar;
+    float *Bhi = Alo + MT * TAPS;                               // [8][NB][4]
+    float *Blo = Bhi + NB * TAPS;
+    float *stage = Blo + NB * TAPS;                             // [8 warps][32][STAGE_LD]
+    float *ex2 = stage + 8 * 32 * STAGE_LD;                     // [2][128]   (row parity)
+    float *ey2 = ex2 + 2 * MT;                                  // [2][NB]    (job parity)
+    float *wbest = ey2 + 2 * NB;                                // [128] WTA hand-over between the two column halves
+    int *wbs = reinterpret_cast<int *>(wbest + MT);             // [128]
+    __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int x0 = blockIdx.x * MT, y = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * MT, h0 = blockIdx.y * RB, b = blockIdx.z;
+    const int rows = min(RB, H - h0);
+    cam += (size_t)b * H * W; proj += (size_t)b * H * W;
     const int p_lo = x0 - (D - 1);
 
     if (warp == 0) {
@@ -93,71 +122,119 @@ __global__ void __launch_bounds__(256) tc_forward(const float *__restrict__ cam,
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 32) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (tid < MT) build_row(cam, H, W, y, x0 + tid, Ahi, Alo, MT, tid, &ex2[tid]);
-    for (int n = tid; n < NP; n += 256) build_row(proj, H, W, y, p_lo + n, Bhi, Blo, NP, n, &ey2[n]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
 
-    if (tid == 0) {
-        // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 160, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
-        const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), b_hi = smem_u32(Bhi), b_lo = smem_u32(Blo);
-        for (int half = 0; half < 2; ++half) {
+    const int q = warp & 3, hh = warp >> 2, m = 32 * q + lane, x = x0 + m;
+    float *my_stage = stage + warp * 32 * STAGE_LD;
+    float bv = -INFINITY;
+    int bs = 0;
+    const int njobs = rows * NBLK;
+
+    for (int j = 0; j <= njobs; ++j) {
+        TICK();
+        if (j > 0) mbar_wait(smem_u32(&mbar[(j - 1) & 1]), ((j - 1) >> 1) & 1);   // MMA j-1 done: operand tiles are free
+        TOCK(t_wait);
+        TICK();
+        if (j < njobs) {
+            const int y = h0 + j / NBLK, blk = j % NBLK;
+            const int nrows_a = blk == 0 ? MT : 0;
+            for (int r = tid; r < nrows_a + NB; r += 256) {
+                if (r < nrows_a) build_row(cam, H, W, y, x0 + r, Ahi, Alo, MT, r, &ex2[((j / NBLK) & 1) * MT + r]);
+                else build_row(proj, H, W, y, p_lo + blk * NB + (r - nrows_a), Bhi, Blo, NB, r - nrows_a, &ey2[(j & 1) * NB + r - nrows_a]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        TOCK(t_build);
+        TICK();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TOCK(t_sync);
+        TICK();
+        if (j < njobs && tid == 0) {
+            const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), b_hi = smem_u32(Bhi), b_lo = smem_u32(Blo);
             uint32_t acc = 0;
-            for (int pass = 3 - passes; pass < 3; ++pass) {   // small terms first: lo*hi, hi*lo, hi*hi
-                const uint32_t a = pass == 0 ? a_lo : a_hi, b = pass == 1 ? b_lo : b_hi;
+            for (int pass = 3 - passes; pass < 3; ++pass) {
+                const uint32_t a = pass == 0 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
+#pragma unroll
                 for (int kk = 0; kk < TAPS / 8; ++kk) {
-                    const uint64_t ad = make_desc(a + kk * 2 * (MT * 16), MT * 16, 128);
-                    const uint64_t bd = make_desc(b + kk * 2 * (NP * 16) + half * NH * 16, NP * 16, 128);
-                    mma_tf32(tmem_base + half * NH, ad, bd, idesc, acc);
+                    mma_tf32(tmem_base + (j & 1) * 256, make_desc(a + kk * 2 * (MT * 16), MT * 16, 128),
+                             make_desc(bb + kk * 2 * (NB * 16), NB * 16, 128), idesc, acc);
                     acc = 1;
                 }
             }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[j & 1])) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
-    }
-    if (warp < 4) {
-        // wait for the accumulators
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int x = x0 + tid;
-        const float e2 = ex2[tid];
-        for (int c0 = 0; c0 < NP; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        TOCK(t_mma);
+        TICK();
+        if (j > 0) {
+            // ---- epilogue of job j-1 (its MMAs completed before this iteration's build) ----
+            const int je = j - 1, y = h0 + je / NBLK, blk = je % NBLK;
+            const int P0 = p_lo + blk * NB + hh * HALF;                       // projector column of this warp's first TMEM column
+            const float e2 = ex2[((je / NBLK) & 1) * MT + m];
+            const float *ey = ey2 + (je & 1) * NB + hh * HALF;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (je & 1) * 256 + hh * HALF;
+            if (blk == 0) { bv = -INFINITY; bs = 0; }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int p = p_lo + c0 + j, s = x - p;
-                if (x < W && s >= 0 && s < D) {
-                    const float exy = __uint_as_float(r[j]);
-                    const float val = p >= 0 ? (exy + kEps) * rsqrtf(fmaf(e2, ey2[c0 + j], kEps)) : -2.f;
-                    out[((size_t)y * W + x) * D + s] = val;
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t r[16];
+                TMEM_LD16(r, taddr + c0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int p = P0 + c0 + jj, s = x - p;
+                    const float val = (__uint_as_float(r[jj]) + kEps) * rsqrtf(fmaf(e2, ey[c0 + jj], kEps));
+                    v[jj] = p >= 0 ? val : -2.f;
+                    if (s >= 0 && s < D && p >= 0 && val > bv) { bv = val; bs = s; }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<float4 *>(my_stage + lane * STAGE_LD + c0 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+            __syncwarp();
+            TOCK(t_math);
+            TICK();
+            // write-out: row i of the stage holds camera column x0 + 32q + i, position n <-> projector column P0 + n
+            for (int i = 0; i < 32; ++i) {
+                const int xr = x0 + 32 * q + i;
+                if (xr >= W) break;
+                const int s_hi = min(D - 1, xr - P0), s_lo = max(0, xr - P0 - (HALF - 1));
+                float *orow = out + (((size_t)b * H + y) * W + xr) * D;
+                for (int s = s_lo + lane; s <= s_hi; s += 32) __stcs(orow + s, my_stage[i * STAGE_LD + (xr - P0 - s)]);
+            }
+            __syncwarp();
+            if (blk == NBLK - 1) {   // row complete: merge the two column halves of every camera column
+                if (hh == 1) { wbest[m] = bv; wbs[m] = bs; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (hh == 0 && x < W) {
+                    const float ov = wbest[m];
+                    const int os = wbs[m];
+                    if (ov > bv || (ov == bv && os > bs)) { bv = ov; bs = os; }
+                    best[((size_t)b * H + y) * W + x] = bv;
+                    index[((size_t)b * H + y) * W + x] = bs;
                 }
             }
         }
+        TOCK(t_out);
+        TICK();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        TOCK(t_sync);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (dbg && blockIdx.x == 3 && blockIdx.y == 3 && blockIdx.z == 0 && (tid == 0 || tid == 200)) {
+        long long *d = dbg + (tid ? 8 : 0);
+        d[0] = t_wait; d[1] = t_build; d[2] = t_mma; d[3] = t_math; d[4] = t_out; d[5] = t_sync; d[6] = njobs;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
@@ -195,12 +272,16 @@ int main() {
     const int H = 375, W = 1242;
     const size_t npx = (size_t)H * W, ncell = npx * D;
     std::vector<float> hc(npx), hp(npx);
-    float *cam, *proj, *out;
+    float *cam, *proj, *out, *best;
+    int *index;
     double *ref;
     const int check_rows = 24;
-    CK(cudaMalloc(&cam, npx * 4)); CK(cudaMalloc(&proj, npx * 4)); CK(cudaMalloc(&out, ncell * 4));
+    CK(cudaMalloc(&cam, npx * 4)); CK(cudaMalloc(&proj, npx * 4)); CK(cudaMalloc(&out, ncell * 4)); CK(cudaMalloc(&best, npx * 4)); CK(cudaMalloc(&index, npx * 4));
     CK(cudaMalloc(&ref, (size_t)check_rows * W * D * 8));
-    const size_t smem = (size_t)(2 * MT * TAPS + 2 * NP * TAPS + MT + NP) * 4;
+    const size_t smem = (size_t)(2 * MT * TAPS + 2 * NB * TAPS + 8 * 32 * STAGE_LD + 2 * MT + 2 * NB + 2 * MT) * 4;
+    const int RB = 25;
+    std::vector<float> hb(npx);
+    std::vector<int> hi(npx);
     CK(cudaFuncSetAttribute(tc_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     std::vector<float> ho(ncell);
     std::vector<double> hr((size_t)check_rows * W * D);
@@ -217,11 +298,13 @@ int main() {
         CK(cudaMemcpy(proj, hp.data(), npx * 4, cudaMemcpyHostToDevice));
         for (int passes = 3; passes >= 1; passes -= 2) {
             CK(cudaMemset(out, 0xff, ncell * 4));
-            dim3 grid((W + MT - 1) / MT, H);
-            tc_forward<<<grid, 256, smem>>>(cam, proj, out, H, W, passes);
+            dim3 grid((W + MT - 1) / MT, (H + RB - 1) / RB, 1);
+            tc_forward<<<grid, 256, smem>>>(cam, proj, out, best, index, H, W, RB, passes, nullptr);
             CK(cudaGetLastError());
             CK(cudaDeviceSynchronize());
-            double worst = 0; size_t bad = 0;
+            double worst = 0; size_t bad = 0, wta_bad = 0;
+            CK(cudaMemcpy(hb.data(), best, npx * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hi.data(), index, npx * 4, cudaMemcpyDeviceToHost));
             for (int y0 : {0, 180, H - check_rows}) {
                 ref_forward<<<(unsigned)(((size_t)check_rows * W * D + 255) / 256), 256>>>(cam, proj, ref, H, W, y0, check_rows);
                 CK(cudaMemcpy(hr.data(), ref, hr.size() * 8, cudaMemcpyDeviceToHost));
@@ -231,17 +314,28 @@ int main() {
                     if (!(e <= 1e-5)) ++bad;
                     if (e > worst || e != e) worst = e;
                 }
+                for (size_t px = 0; px < (size_t)check_rows * W; ++px) {   // WTA = arg-max of the kernel's own volume, ties -> largest s
+                    float m = -INFINITY; int ms = 0;
+                    for (int s = D - 1; s >= 0; --s) if (ho[px * D + s] > m && ho[px * D + s] != -2.f) { m = ho[px * D + s]; ms = s; }
+                    const size_t gp = (size_t)y0 * W + px;
+                    if (hb[gp] != m || hi[gp] != ms) ++wta_bad;
+                }
             }
-            printf("family %d  %d-pass tf32: max |cost - fp64| = %.3e over %zu cells, %zu above 1e-5\n", family, passes,
-                   worst, 3 * hr.size(), bad);
+            printf("family %d  %d-pass tf32: max |cost - fp64| = %.3e over %zu cells, %zu above 1e-5, %zu WTA mismatches\n", family, passes,
+                   worst, 3 * hr.size(), bad, wta_bad);
         }
     }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    dim3 grid((W + MT - 1) / MT, H);
+    dim3 grid((W + MT - 1) / MT, (H + RB - 1) / RB, 1);
+    long long *dbg; CK(cudaMalloc(&dbg, 16 * 8)); CK(cudaMemset(dbg, 0, 16 * 8));
     cudaEventRecord(e0);
-    for (int it = 0; it < 10; ++it) tc_forward<<<grid, 256, smem>>>(cam, proj, out, H, W, 3);
+    for (int it = 0; it < 10; ++it) tc_forward<<<grid, 256, smem>>>(cam, proj, out, best, index, H, W, RB, 3, dbg);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("prototype (one row tile per CTA, scalar stores, no pipelining): %.3f ms per pair = %.1f Gcell/s\n", ms / 10, ncell / (ms / 10) * 1e-6);
+    long long hd[16]; CK(cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < 2; ++t)
+        printf("thread %d clocks per job: wait %lld  build %lld  mma-issue %lld  math %lld  write-out %lld  sync %lld  (jobs %lld)\n", t ? 200 : 0,
+               hd[8 * t] / hd[8 * t + 6], hd[8 * t + 1] / hd[8 * t + 6], hd[8 * t + 2] / hd[8 * t + 6], hd[8 * t + 3] / hd[8 * t + 6], hd[8 * t + 4] / hd[8 * t + 6], hd[8 * t + 5] / hd[8 * t + 6], hd[8 * t + 6]);
+    printf("prototype v2 (banded, MMA overlapped with the epilogue, staged stores, WTA): %.3f ms per pair = %.1f Gcell/s\n", ms / 10, ncell / (ms / 10) * 1e-6);
     return 0;
 }
