@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_NAME = "libcustma_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
-SOURCES = ["custma_api.cu", "direct.cu", "sliding_prep.cu", "sliding_forward.cu", "sliding_backward.cu", "sliding_fallback.cu", "tc_forward.cu", "host_pipeline.cu"]
+SOURCES = ["custma_api.cu", "direct.cu", "sliding_prep.cu", "sliding_forward.cu", "sliding_backward.cu", "sliding_fallback.cu", "tc_forward.cu", "tc_backward.cu", "host_pipeline.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -72,6 +72,12 @@ bool tc_forward_supported(const Problem &p);
 int launch_tc_forward(const Problem &p, const float *cam, const float *proj, float *cost, unsigned long long *keys,
                       const uint32_t *fb_count, uint32_t threshold, cudaStream_t stream);
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
-                            float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                            float *camera_grad, void *workspace, size_t workspace_bytes, bool force_tensor,
+                            cudaStream_t stream);
+// tensor-core backward (tc_backward.cu): runs when fb_count is NULL or *fb_count > threshold, then writes camera_grad
+bool tc_backward_supported(const Problem &p);
+size_t tc_backward_scratch_bytes(const Problem &p);
+int launch_tc_backward(const Problem &p, const float *grad, const float *cam, const float *proj, float *camera_grad,
+                       float *scratch, const uint32_t *fb_count, uint32_t threshold, cudaStream_t stream);
 
 }  // namespace custma

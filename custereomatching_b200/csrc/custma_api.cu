@@ -144,8 +144,11 @@ int custma_backward(const float *cost_volume_grad, const float *camera, const fl
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
     if ((rc = carve_stats(p, workspace, workspace_bytes, backward_ws(p, flags), &s))) return rc;
+    if ((flags & CUSTMA_FLAG_TENSOR) && ((flags & CUSTMA_FLAG_DIRECT) || !tc_backward_supported(p) || !sliding_backward_supported(p)))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 540, k = 3 or 5, and no CUSTMA_FLAG_DIRECT");
     if (use_sliding_bwd(p, flags))
-        return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, s.rest, s.rest_bytes, stream);
+        return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, s.rest, s.rest_bytes,
+                                       (flags & CUSTMA_FLAG_TENSOR) != 0, stream);
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,

@@ -375,12 +375,14 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 template <int K, int NU, int WG>
 __global__ void __launch_bounds__(16 * NU * WG, 1)
     sliding_backward_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
-                            const float *__restrict__ grad) {
+                            const float *__restrict__ grad, const uint32_t tc_threshold) {
     using F = SlideGeom<K, NU, WG>;
     constexpr int WTC = F::WTC, SC = F::SC, NS = F::NS, NCW = F::NCW;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
 
+    // so many flagged tiles that the tensor-core kernel (tc_backward.cu) computes the whole call
+    if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
     const int tid = threadIdx.x;
     const int wt = blockIdx.x / L.n_chunks, ch = blockIdx.x % L.n_chunks, nb = blockIdx.y, b = blockIdx.z;
     const int w_base = wt * WTC, s_base = chunk_s_base(L, p.W, w_base, ch), h0 = nb * L.RB;
@@ -451,7 +453,8 @@ __device__ __forceinline__ int div_near(int x, int d, int q0) {   // q0 * d <= x
 template <int K>
 __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
-                                     const char *__restrict__ ws, float *__restrict__ camera_grad) {
+                                     const char *__restrict__ ws, float *__restrict__ camera_grad, const uint32_t tc_threshold) {
+    if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
     constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinTY + K - 1;
     static_assert(SH <= 2 * kFinTY && SW <= 2 * kFinTX, "two passes of the thread block cover the staged cells");
     __shared__ float q1[SH][SW + 1], q2[SH][SW + 1];
@@ -563,24 +566,24 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
 
 template <int K, int NU, int WG>
 static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws, const float *grad,
-                          cudaStream_t stream) {
+                          uint32_t thr, cudaStream_t stream) {
     const size_t smem = BwdGeom<K, NU, WG>::SMEM_BYTES;
     auto kern = sliding_backward_kernel<K, NU, WG>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad);
+    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad, thr);
     CUSTMA_LAUNCH_CHECK("sliding_backward_kernel");
     return CUSTMA_OK;
 }
 
 template <int K>
 static int launch_bwd_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws,
-                        const float *grad, cudaStream_t stream) {
+                        const float *grad, uint32_t thr, cudaStream_t stream) {
     switch (cfg.NU) {
-        case 1: return launch_bwd_cfg<K, 1, 16>(p, L, BL, ws, grad, stream);
-        case 2: return launch_bwd_cfg<K, 2, 8>(p, L, BL, ws, grad, stream);
-        case 3: return launch_bwd_cfg<K, 3, 5>(p, L, BL, ws, grad, stream);
-        default: return launch_bwd_cfg<K, 4, 4>(p, L, BL, ws, grad, stream);
+        case 1: return launch_bwd_cfg<K, 1, 16>(p, L, BL, ws, grad, thr, stream);
+        case 2: return launch_bwd_cfg<K, 2, 8>(p, L, BL, ws, grad, thr, stream);
+        case 3: return launch_bwd_cfg<K, 3, 5>(p, L, BL, ws, grad, thr, stream);
+        default: return launch_bwd_cfg<K, 4, 4>(p, L, BL, ws, grad, thr, stream);
     }
 }
 
@@ -596,29 +599,43 @@ size_t sliding_backward_workspace_bytes(const Problem &p) {
     make_sliding_layout(p, cfg, true, &L);
     BwdLayout BL;
     make_bwd_layout(p, L, &BL);
-    return BL.total;
+    return align256(BL.total) + tc_backward_scratch_bytes(p);
 }
 
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
-                            float *camera_grad, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            float *camera_grad, void *workspace, size_t workspace_bytes, bool force_tensor,
+                            cudaStream_t stream) {
     SlidingConfig cfg;
     if (!sliding_pick_config(p, true, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
     make_sliding_layout(p, cfg, true, &L);
     BwdLayout BL;
     make_bwd_layout(p, L, &BL);
-    if (workspace_bytes < BL.total)
-        return set_error(CUSTMA_ERR_WORKSPACE, "sliding backward needs %zu workspace bytes, %zu given", BL.total, workspace_bytes);
+    const size_t need = align256(BL.total) + tc_backward_scratch_bytes(p);
+    if (workspace_bytes < need)
+        return set_error(CUSTMA_ERR_WORKSPACE, "sliding backward needs %zu workspace bytes, %zu given", need, workspace_bytes);
     char *ws = (char *)workspace;
+    float *tc_scratch = (float *)(ws + align256(BL.total));
+    if (force_tensor) {
+        if (!tc_backward_supported(p))
+            return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 540 and k = 3 or 5");
+        return launch_tc_backward(p, grad, cam, proj, camera_grad, tc_scratch, nullptr, 0, stream);
+    }
     int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
     if (rc) return rc;
-    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, stream) : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, stream);
+    // same cross-over as the forward (sliding_forward.cu): above this share of flagged work the tensor-core kernel
+    // computes the whole call and the sliding / fallback / finalize kernels return at once
+    const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;
+    const uint32_t thr = tc_backward_supported(p) ? (uint32_t)(0.04 * items) : 0xffffffffu;
+    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, thr, stream) : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, thr, stream);
     if (rc) return rc;
-    if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), stream))) return rc;
+    if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
     const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B), fblock(kFinTX, kFinTY);
-    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad);
-    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad);
+    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
+    if (thr != 0xffffffffu)
+        return launch_tc_backward(p, grad, cam, proj, camera_grad, tc_scratch, (const uint32_t *)(ws + L.off_fb_count), thr, stream);
     return CUSTMA_OK;
 }
 

@@ -284,6 +284,7 @@ int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const floa
                             const char *ws, float *cost, unsigned long long *keys, uint32_t tc_threshold,
                             cudaStream_t stream);
 int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
-                               const float *proj, const char *ws, float *patch_grad, cudaStream_t stream);
+                               const float *proj, const char *ws, float *patch_grad, uint32_t tc_threshold,
+                               cudaStream_t stream);
 
 }  // namespace custma

@@ -142,9 +142,10 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                                const float *__restrict__ cam, const float *__restrict__ proj,
                                const uint8_t *__restrict__ flags, const uint32_t *__restrict__ fb_count,
                                const uint32_t *__restrict__ fb_list, const float *__restrict__ fb_pm,
-                               const float *__restrict__ fb_ey2, float *__restrict__ patch_grad) {
+                               const float *__restrict__ fb_ey2, float *__restrict__ patch_grad, const uint32_t tc_threshold) {
     extern __shared__ float smem[];
     const uint32_t n_items = *fb_count;
+    if (n_items > tc_threshold) return;   // the tensor-core kernel computes the whole call
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const uint32_t code = fb_list[item];
     const int64_t t3 = code / L.fb_groups;
@@ -229,7 +230,8 @@ int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const floa
 size_t fallback_backward_smem(const Problem &p) { return (size_t)kFbWarps * (p.k * p.k + 2 * p.C) * sizeof(float); }
 
 int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
-                               const float *proj, const char *ws, float *patch_grad, cudaStream_t stream) {
+                               const float *proj, const char *ws, float *patch_grad, uint32_t tc_threshold,
+                               cudaStream_t stream) {
     const size_t smem = fallback_backward_smem(p);
     if (smem > 200 * 1024)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback backward: last axis %d too long for shared memory", p.C);
@@ -240,7 +242,7 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
     fallback_patch_grad_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
         p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2),
-        patch_grad);
+        patch_grad, tc_threshold);
     CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");
     return CUSTMA_OK;
 }

@@ -55,9 +55,10 @@ extern "C" {
 /* flags */
 #define CUSTMA_FLAG_DIRECT 1u /* force the direct two-pass kernels (reference arithmetic order; forward is bit-exact
                                  with the reference extension).  Default: sliding-window kernels where available. */
-#define CUSTMA_FLAG_TENSOR 2u /* forward only: force the tensor-core (tcgen05, 3xTF32) kernel, which the default path
-                                 otherwise picks by itself for ill-conditioned (low-texture) inputs.  Needs a banded
-                                 volume with D % 4 == 0, D <= 572 and k = 3 or 5; CUSTMA_ERR_UNSUPPORTED otherwise. */
+#define CUSTMA_FLAG_TENSOR 2u /* force the tensor-core (tcgen05, 3xTF32) kernels, which the default path otherwise picks
+                                 by itself for ill-conditioned (low-texture) inputs.  Needs a banded volume with
+                                 D % 4 == 0, D <= 572 (forward) / 540 (backward) and k = 3 or 5;
+                                 CUSTMA_ERR_UNSUPPORTED otherwise. */
 
 int custma_abi_version(void);
 const char *custma_last_error(void);

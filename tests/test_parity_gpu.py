@@ -471,6 +471,9 @@ def test_fuzz_fast_path_against_direct_path():
         g0 = cb.backward(g, cam, proj, k, D, flags=cb.FLAG_DIRECT)
         g1 = cb.backward(g, cam, proj, k, D)
         assert_grad_close(g1.cpu().numpy(), g0.cpu().numpy(), what=tag + " grad", tol=2e-5)
+        if D > 0 and D % 4 == 0 and k in (3, 5):
+            g2 = cb.backward(g, cam, proj, k, D, flags=cb.FLAG_TENSOR)
+            assert_grad_close(g2.cpu().numpy(), g0.cpu().numpy(), what=tag + " tensor-core grad", tol=2e-5)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -545,3 +548,53 @@ def test_verdict_hands_low_texture_inputs_to_the_tensor_core_kernel():
     c_tc = cb.cost_volume(dev(cam), dev(proj), D, k, flags=cb.FLAG_TENSOR)
     assert not torch.equal(c_def, c_tc)
     assert_cost_close(c_def.cpu().numpy(), c_tc.cpu().numpy())
+
+
+# (the 1 x 1 image is left out: its gradient is mathematically zero, so there is no scale to compare rounding noise with)
+@pytest.mark.parametrize("H,W,D,k", [c for c in TENSOR_CASES if c[2] <= 540 and c[0] * c[1] > 1])
+def test_tensor_core_backward_vs_oracle(H, W, D, k):
+    cam, proj = rand_pair(H, W, seed=H * 1000 + W + 2)
+    gb = np.random.RandomState(H + W).randn(H, W, D).astype(np.float32)
+    gref = ref_port.backward_banded(gb, cam, proj, k)
+    grad = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=cb.FLAG_TENSOR)
+    assert_grad_close(grad.cpu().numpy(), gref)
+    again = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=cb.FLAG_TENSOR)
+    assert torch.equal(grad, again)                       # deterministic: no atomics anywhere
+
+
+def test_tensor_core_backward_batched_equals_per_pair_and_autograd():
+    B, H, W, D, k = 3, 50, 300, 128, 5
+    cam, proj = rand_pair(H, W, seed=78, B=B)
+    g = torch.from_numpy(np.random.RandomState(1).randn(B, H, W, D).astype(np.float32)).cuda()
+    grad = cb.backward(g, dev(cam), dev(proj), k, D, flags=cb.FLAG_TENSOR)
+    for b in range(B):
+        g1 = cb.backward(g[b].contiguous(), dev(cam[b]), dev(proj[b]), k, D, flags=cb.FLAG_TENSOR)
+        assert torch.equal(grad[b], g1)
+    c = dev(cam).requires_grad_(True)
+    cb.cost_volume(c, dev(proj), D, k, flags=cb.FLAG_TENSOR).backward(g)
+    assert torch.equal(c.grad, grad)
+    with pytest.raises(RuntimeError):
+        cb.backward(torch.zeros(16, 40, 544, device="cuda"), dev(cam[0][:16, :40].copy()), dev(proj[0][:16, :40].copy()), k, 544,
+                    flags=cb.FLAG_TENSOR)
+
+
+def test_verdict_hands_low_texture_backward_to_the_tensor_core_kernel():
+    H, W, D, k = 64, 420, 192, 5
+    rng = np.random.RandomState(6)
+    xx = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)
+    yy = np.arange(H, dtype=np.float32)[:, None].repeat(W, 1)
+    scene = lambda sh: 0.5 + 0.4 * np.sin((xx + sh) * 0.01) * np.cos(yy * 0.02)
+    cam = np.ascontiguousarray(scene(0) + 0.02 * (rng.rand(H, W) - 0.5), np.float32)
+    proj = np.ascontiguousarray(scene(40) + 0.02 * (rng.rand(H, W) - 0.5), np.float32)
+    gb = rng.randn(H, W, D).astype(np.float32)
+    g_def = cb.backward(dev(gb), dev(cam), dev(proj), k, D)
+    g_tc = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=cb.FLAG_TENSOR)
+    assert torch.equal(g_def, g_tc)
+    gref = ref_port.backward_banded(gb, cam, proj, k)
+    truth = zo.camera_grad_banded_autograd(cam, proj, gb, D, k).numpy()
+    assert_grad_close_or_nearer_truth(g_def.cpu().numpy(), gref, truth)
+    cam, proj = rand_pair(H, W, seed=10)                  # textured: the sliding-window kernels keep the call
+    g_def = cb.backward(dev(gb), dev(cam), dev(proj), k, D)
+    g_tc = cb.backward(dev(gb), dev(cam), dev(proj), k, D, flags=cb.FLAG_TENSOR)
+    assert not torch.equal(g_def, g_tc)
+    assert_grad_close(g_def.cpu().numpy(), g_tc.cpu().numpy())
