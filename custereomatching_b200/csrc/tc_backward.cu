@@ -281,6 +281,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             if (n - f >= 0) S.ey2[f][n - f] = e;
                     }
                     if (blk == nblk - 1) load_ring_row<KW>(S, cam, proj, H, W, y + R + 1, cam_x0, prj_x0, prj_w, tid);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fence_before();
+                    bar_arrive(smem_u32(&S.ops1_bar));
+                    // (the tensor core now runs MMA1; the gradient tile is fetched meanwhile)
                     // gradient tile of this job -> stage (same slots as the forward's write-out), zeros where no cell exists
                     if (tid < 18 * NQ) {
                         const int g4 = tid % NQ, row0 = tid / NQ;
@@ -298,9 +302,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             }
                         }
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    fence_before();
-                    bar_arrive(smem_u32(&S.ops1_bar));
                     worker_sync();                                   // stage and ey2 / ex2 are complete
                     bar_wait(smem_u32(&S.mma1_bar), J & 1);
                     fence_after();
@@ -399,11 +400,11 @@ __global__ void __launch_bounds__(256)
     tc_backward_finalize_kernel(const Problem p, const int R, const int n_bands, const uint32_t *__restrict__ fb_count,
                                 const uint32_t threshold, const float *__restrict__ scratch, float *__restrict__ out) {
     if (fb_count != nullptr && *fb_count <= threshold) return;
-    const int B = p.B, H = p.H, W = p.W;
-    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (int64_t)B * H * W) return;
-    const int x = id % W, y = (id / W) % H, b = id / ((int64_t)W * H);
+    const int H = p.H, W = p.W;
     const int n_xt = (W + MT - 1) / MT;
+    // grid-stride: a fixed small grid, so the launch costs nothing when the kernel is not needed
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < p.pixels(); id += (int64_t)gridDim.x * blockDim.x) {
+    const int x = id % W, y = (id / W) % H, b = id / ((int64_t)W * H);
     float acc = 0.f;
     for (int nb = max(0, y / RB - 1); nb <= min(n_bands - 1, y / RB + 1); ++nb) {
         const int row = y - (nb * RB - R);
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(256)
         }
     }
     out[id] = acc;
+    }
 }
 
 
@@ -431,7 +433,7 @@ static int launch_k(const Problem &p, const float *grad, const float *cam, const
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)std::min<int64_t>(n_tiles, n_sm), NTHREADS, smem, stream>>>(p, n_bands, fb_count, threshold, cam, proj, grad, scratch);
     CUSTMA_LAUNCH_CHECK("tc_backward_kernel");
-    tc_backward_finalize_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, KW / 2, n_bands, fb_count, threshold, scratch, camera_grad);
+    tc_backward_finalize_kernel<<<(unsigned)std::min<int64_t>((p.pixels() + 255) / 256, 8 * n_sm), 256, 0, stream>>>(p, KW / 2, n_bands, fb_count, threshold, scratch, camera_grad);
     CUSTMA_LAUNCH_CHECK("tc_backward_finalize_kernel");
     return CUSTMA_OK;
 }
