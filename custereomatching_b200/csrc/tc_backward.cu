@@ -58,9 +58,9 @@ struct Smem {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// round to nearest tf32 (the tensor core itself truncates the low 13 mantissa bits): the residual v - hi then has at most
-// 12 significant bits and loses at most one of them when it is used as the second tf32 operand
-__device__ __forceinline__ float tf32_hi(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); }
+// upper tf32 half, rounded to nearest (half away from zero) with two integer instructions - the tensor core itself would
+// truncate the low 13 mantissa bits; the residual v - hi then has at most 12 significant bits
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 0) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | (uint64_t)(lbo_bytes >> 4) << 16 | (uint64_t)(sbo_bytes >> 4) << 32 | 1ull << 46 | (uint64_t)layout << 61;
 }

@@ -44,6 +44,7 @@ def test_header_constants_match_binding():
     assert f"#define CUSTMA_ABI_VERSION {binding.ABI_VERSION}" in text
     assert "#define CUSTMA_INVALID_COST (-2.0f)" in text and binding.INVALID_COST == -2.0
     assert "#define CUSTMA_FLAG_DIRECT 1u" in text and binding.FLAG_DIRECT == 1
+    assert "#define CUSTMA_FLAG_TENSOR 2u" in text and binding.FLAG_TENSOR == 2
 
 
 @pytest.mark.parametrize("args", [(0, 4, 4, 0, 5), (1, 0, 4, 0, 5), (1, 4, 4, -1, 5), (1, 4, 4, 0, 0), (1, 4, 4, 0, 32)])
@@ -57,6 +58,9 @@ def test_workspace_query_accepts_good_arguments():
     assert binding.forward_workspace_bytes(1, 240, 320, 64, 5) > 0
     assert binding.backward_workspace_bytes(2, 375, 1242, 192, 5) > 0
     assert binding.forward_workspace_bytes(1, 240, 320, 0, 15, binding.FLAG_DIRECT) > 0
+    # the backward workspace holds the tensor-core kernel's halo tiles wherever that kernel can take the call
+    assert binding.backward_workspace_bytes(1, 64, 256, 64, 5) > binding.backward_workspace_bytes(1, 64, 256, 62, 5) - 64 * 256 * 8
+    assert binding.forward_workspace_bytes(1, 240, 320, 64, 5, binding.FLAG_TENSOR) > 0
 
 
 def test_null_pointers_are_rejected_before_any_cuda_call():
