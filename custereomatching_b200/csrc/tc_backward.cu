@@ -34,7 +34,7 @@ constexpr int RING = 6, CAMW = 136, PRW = 696;
 constexpr int RB = 16, GW = MT + 4;           // rows per tile, width of the tile's gradient image
 constexpr int kMaxBlocks = 6, kMaxD = kMaxBlocks * PW - 131;
 constexpr int NWORK = 512, NTHREADS = NWORK + 32;
-constexpr int COL_AH = 0, COL_AL = NT, COL_G1 = 2 * NT;   // TMEM columns: D1 / A_hi, A_lo, G1
+constexpr int COL_D1 = 0, COL_AH = NT, COL_AL = 2 * NT, COL_G1 = 3 * NT;   // TMEM columns: D1, A_hi, A_lo, G1 (416 of 512)
 
 template <int KW>
 struct Geom {
@@ -46,7 +46,8 @@ struct Smem {
     using G = Geom<KW>;
     float Ahi[G::CH][MT][4], Alo[G::CH][MT][4];
     float Bhi[G::CH][NT][4], Blo[G::CH][NT][4];   // PC, K-major (MMA1)
-    float B2hi[NT][TAPS2], B2lo[NT][TAPS2];        // PC, MN-major with the 32-byte-base swizzle (MMA2)
+    float B2hi[2][NT][TAPS2], B2lo[2][NT][TAPS2];  // PC, MN-major with the 32-byte-base swizzle (MMA2); by job parity,
+                                                   // so that MMA2 of job j runs while job j+1 is being built
     float stage[MT][SLD];                          // cost_volume_grad tile of the job
     float camring[RING][CAMW], prjring[RING][PRW];
     float gring[RB + 4][GW];                       // the tile's camera-gradient image incl. halo
@@ -202,13 +203,22 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const uint32_t tmem_base = S.tmem_base;
 
     uint32_t J = 0;
+    if (warp < NWORK / 32) {
+        // A_hi / A_lo columns outside a warp quadrant's window [phi, phi + PW) are never written by the epilogue: zero once
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        const uint32_t zeros[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if ((warp >> 2) == 0) { tmem_st4(lane_addr + COL_AH, zeros); tmem_st4(lane_addr + COL_AL, zeros); }
+        if ((warp >> 2) == 3) { tmem_st16(lane_addr + COL_AH + PW, zeros); tmem_st16(lane_addr + COL_AL + PW, zeros); }
+        tmem_wait_st();
+        fence_before();
+    }
     if (warp == NWORK / 32) {
         // ================= MMA warp =================
         const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
         // MMA2: N = 32 taps, B operand MN-major (bit 16)
         const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(TAPS2 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
         const uint32_t a_hi = smem_u32(S.Ahi), a_lo = smem_u32(S.Alo), b_hi = smem_u32(S.Bhi), b_lo = smem_u32(S.Blo);
-        const uint32_t b2_hi = smem_u32(S.B2hi), b2_lo = smem_u32(S.B2lo);
+        const uint32_t b2_hi[2] = {smem_u32(S.B2hi[0]), smem_u32(S.B2hi[1])}, b2_lo[2] = {smem_u32(S.B2lo[0]), smem_u32(S.B2lo[1])};
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int nb = (int)((tile / n_xt) % n_bands);
             const int rows = min(RB, H - nb * RB);
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                             const uint32_t a = pass == 0 ? a_lo : a_hi, bb = pass == 1 ? b_lo : b_hi;
 #pragma unroll
                             for (int kk = 0; kk < TAPS / 8; ++kk) {
-                                mma_ss(tmem_base + COL_AH, make_desc(a + kk * 2 * (MT * 16), MT * 16, 128),
+                                mma_ss(tmem_base + COL_D1, make_desc(a + kk * 2 * (MT * 16), MT * 16, 128),
                                        make_desc(bb + kk * 2 * (NT * 16), NT * 16, 128), idesc1, acc);
                                 acc = 1;
                             }
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         uint32_t acc = blk == 0 ? 0u : 1u;
 #pragma unroll 1
                         for (int pass = 0; pass < 3; ++pass) {   // A_lo*PC_hi, A_hi*PC_lo, A_hi*PC_hi
-                            const uint32_t ta = tmem_base + (pass == 0 ? COL_AL : COL_AH), bb = pass == 1 ? b2_lo : b2_hi;
+                            const uint32_t ta = tmem_base + (pass == 0 ? COL_AL : COL_AH), bb = pass == 1 ? b2_lo[J & 1] : b2_hi[J & 1];
 #pragma unroll 4
                             for (int kk = 0; kk < NT / 8; ++kk) {
                                 mma_ts(tmem_base + COL_G1, ta + kk * 8, make_desc(bb + kk * 1024, 0, 512, 1), idesc2, acc);
@@ -268,14 +278,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 const int y = h0 + r;
                 float bsum = 0.f;
                 for (int blk = 0; blk < nblk; ++blk, ++J) {
-                    if (J > 0) bar_wait(smem_u32(&S.mma2_bar), (J - 1) & 1);   // MMA2 of the previous job no longer reads PC / A / TMEM
+                    worker_sync();   // every worker is done with the previous job's stage / ey2; its GEMM 1 has been waited for
                     const int nA = blk == 0 ? MT : 0;
                     if (tid < nA) {
                         const int col0 = 4 * (tid & 31) + (tid >> 5);
                         S.ex2[tid] = build_patch<KW, MT>(&S.camring[0][0], CAMW, y, col0, S.Ahi, S.Alo, tid);
                     } else if (tid < nA + NT) {
                         const int n = tid - nA;
-                        const float e = build_patch<KW, NT>(&S.prjring[0][0], PRW, y, p_span - blk * PW - n, S.Bhi, S.Blo, n, S.B2hi, S.B2lo);
+                        const float e = build_patch<KW, NT>(&S.prjring[0][0], PRW, y, p_span - blk * PW - n, S.Bhi, S.Blo, n, S.B2hi[J & 1], S.B2lo[J & 1]);
 #pragma unroll
                         for (int f = 0; f < 4; ++f)
                             if (n - f >= 0) S.ey2[f][n - f] = e;
@@ -303,15 +313,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         }
                     }
                     worker_sync();                                   // stage and ey2 / ex2 are complete
-                    bar_wait(smem_u32(&S.mma1_bar), J & 1);
-                    fence_after();
+                    bar_wait(smem_u32(&S.mma1_bar), J & 1);   // GEMM 1 of this job - and, the tensor core running in order, GEMM 2 of the
+                    fence_after();                           // previous one: A_hi / A_lo may be overwritten
                     // ---- epilogue 1 ----
                     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
                     const float e2 = S.ex2[L];
                     const float4 *ey = reinterpret_cast<const float4 *>(&S.ey2[phi][NQ * cq]);
                     const float4 *gs = reinterpret_cast<const float4 *>(&S.stage[L][NQ * cq]);
                     const int p_first = P_top4 - (blk * PW + col_first);
-                    const uint32_t t_ah = lane_addr + COL_AH + col_first, t_al = lane_addr + COL_AL + col_first;
+                    const uint32_t t_d1 = lane_addr + COL_D1 + col_first, t_ah = lane_addr + COL_AH + col_first, t_al = lane_addr + COL_AL + col_first;
                     uint32_t d[16], dl[4], ah[16], al[16];
                     auto proc = [&](const uint32_t *dd, int i0, int n) {
 #pragma unroll
@@ -335,19 +345,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         else if (n == 8) { tmem_st8(t_ah + i0, ah); tmem_st8(t_al + i0, al); }
                         else { tmem_st4(t_ah + i0, ah); tmem_st4(t_al + i0, al); }
                     };
-                    tmem_ld4(dl, t_ah + 24);
-                    tmem_ld16(d, t_ah);
+                    tmem_ld16(d, t_d1);
+                    tmem_ld4(dl, t_d1 + 24);
                     tmem_wait_ld();
-                    // columns outside [phi, phi + 176) carry no cells of this job: zero them in both A halves (the D1
-                    // columns this overwrites are already in this thread's registers)
-                    {
-                        const uint32_t zeros[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                        if (cq == 0) { tmem_st4(lane_addr + COL_AH, zeros); tmem_st4(lane_addr + COL_AL, zeros); }
-                        if (cq == 3) { tmem_st16(lane_addr + COL_AH + PW, zeros); tmem_st16(lane_addr + COL_AL + PW, zeros); }
-                        tmem_wait_st();
-                    }
                     proc(d, 0, 16);
-                    tmem_ld8(d, t_ah + 16); tmem_wait_ld();
+                    tmem_ld8(d, t_d1 + 16); tmem_wait_ld();
                     proc(d, 16, 8);
                     proc(dl, 24, 4);
                     tmem_wait_st();
