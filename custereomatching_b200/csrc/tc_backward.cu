@@ -31,7 +31,7 @@ constexpr int PW = 112, NT = 128;             // projector columns processed / c
 constexpr int NQ = PW / 4, SLD = PW + 4;      // columns per worker warp, stage pitch
 constexpr int TAPS2 = 32;                     // MMA2 N: window taps padded to one 128-byte row
 constexpr int RING = 6, CAMW = 136, PRW = 696;
-constexpr int RB = 16, GW = MT + 4;           // rows per tile, width of the tile's gradient image
+constexpr int RBMAX = 16, GW = MT + 4;        // most rows per tile, width of the tile's gradient image
 constexpr int kMaxBlocks = 6, kMaxD = kMaxBlocks * PW - 131;
 constexpr int NWORK = 512, NTHREADS = NWORK + 32;
 constexpr int COL_D1 = 0, COL_AH = NT, COL_AL = 2 * NT, COL_G1 = 3 * NT;   // TMEM columns: D1, A_hi, A_lo, G1 (416 of 512)
@@ -50,7 +50,7 @@ struct Smem {
                                                    // so that MMA2 of job j runs while job j+1 is being built
     float stage[MT][SLD];                          // cost_volume_grad tile of the job
     float camring[RING][CAMW], prjring[RING][PRW];
-    float gring[RB + 4][GW];                       // the tile's camera-gradient image incl. halo
+    float gring[RBMAX + 4][GW];                       // the tile's camera-gradient image incl. halo
     float ex2[MT];
     float ey2[4][NT + 4];
     float bs[4][MT];
@@ -169,7 +169,7 @@ __device__ __forceinline__ float build_patch(const float *ring, int pitch, int y
 
 template <int KW>
 __global__ void __launch_bounds__(NTHREADS, 1)
-    tc_backward_kernel(const Problem p, const int n_bands, const uint32_t *__restrict__ fb_count, const uint32_t threshold,
+    tc_backward_kernel(const Problem p, const int RB, const int n_bands, const uint32_t *__restrict__ fb_count, const uint32_t threshold,
                        const float *__restrict__ cam_all, const float *__restrict__ proj_all, const float *__restrict__ grad,
                        float *__restrict__ scratch) {
     using G = Geom<KW>;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const int cam_x0 = x0 - R, prj_x0 = P_top4 - p_span - R;
             worker_sync();
             for (int yy = h0 - R; yy <= h0 + R; ++yy) load_ring_row<KW>(S, cam, proj, H, W, yy, cam_x0, prj_x0, prj_w, tid);
-            for (int i = tid; i < (RB + 4) * GW; i += NWORK) (&S.gring[0][0])[i] = 0.f;
+            for (int i = tid; i < (RBMAX + 4) * GW; i += NWORK) (&S.gring[0][0])[i] = 0.f;
             worker_sync();
             for (int r = 0; r < rows; ++r) {
                 const int y = h0 + r;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
 // camera_grad[b, y, x] = sum of the (up to 3 x 2) tiles whose gradient image covers the pixel, in a fixed order
 __global__ void __launch_bounds__(256)
-    tc_backward_finalize_kernel(const Problem p, const int R, const int n_bands, const uint32_t *__restrict__ fb_count,
+    tc_backward_finalize_kernel(const Problem p, const int R, const int RB, const int n_bands, const uint32_t *__restrict__ fb_count,
                                 const uint32_t threshold, const float *__restrict__ scratch, float *__restrict__ out) {
     if (fb_count != nullptr && *fb_count <= threshold) return;
     const int H = p.H, W = p.W;
@@ -422,20 +422,34 @@ __global__ void __launch_bounds__(256)
 }
 
 
+// Rows per tile: the fewest rounds of tiles over the persistent CTAs (148 assumed: the workspace query must give the
+// same answer without a device), little per-tile start-up (ring fill, halo rows).
+static int pick_rows(const Problem &p) {
+    const int64_t per_row = (int64_t)p.B * ((p.W + MT - 1) / MT);
+    int best_rb = RBMAX;
+    double best_cost = 1e30;
+    for (int rb = RBMAX; rb >= 4; --rb) {
+        const int64_t tiles = per_row * ((p.H + rb - 1) / rb);
+        const double c = (double)((tiles + 147) / 148) * (rb + 2.0);
+        if (c < best_cost) { best_cost = c; best_rb = rb; }
+    }
+    return best_rb;
+}
+
 template <int KW>
 static int launch_k(const Problem &p, const float *grad, const float *cam, const float *proj, float *camera_grad,
                     float *scratch, const uint32_t *fb_count, uint32_t threshold, cudaStream_t stream) {
     int dev = 0, n_sm = 148;
     CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
     CUSTMA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_bands = (p.H + RB - 1) / RB;
+    const int RB = pick_rows(p), n_bands = (p.H + RB - 1) / RB;
     const int64_t n_tiles = (int64_t)p.B * n_bands * ((p.W + MT - 1) / MT);
     auto kern = tc_backward_kernel<KW>;
     const size_t smem = sizeof(Smem<KW>);
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)std::min<int64_t>(n_tiles, n_sm), NTHREADS, smem, stream>>>(p, n_bands, fb_count, threshold, cam, proj, grad, scratch);
+    kern<<<(unsigned)std::min<int64_t>(n_tiles, n_sm), NTHREADS, smem, stream>>>(p, RB, n_bands, fb_count, threshold, cam, proj, grad, scratch);
     CUSTMA_LAUNCH_CHECK("tc_backward_kernel");
-    tc_backward_finalize_kernel<<<(unsigned)std::min<int64_t>((p.pixels() + 255) / 256, 8 * n_sm), 256, 0, stream>>>(p, KW / 2, n_bands, fb_count, threshold, scratch, camera_grad);
+    tc_backward_finalize_kernel<<<(unsigned)std::min<int64_t>((p.pixels() + 255) / 256, 8 * n_sm), 256, 0, stream>>>(p, KW / 2, RB, n_bands, fb_count, threshold, scratch, camera_grad);
     CUSTMA_LAUNCH_CHECK("tc_backward_finalize_kernel");
     return CUSTMA_OK;
 }
@@ -448,8 +462,9 @@ bool tc_backward_supported(const Problem &p) {
 
 size_t tc_backward_scratch_bytes(const Problem &p) {
     if (!tc_backward_supported(p)) return 0;
-    const int64_t n_tiles = (int64_t)p.B * ((p.H + tcb::RB - 1) / tcb::RB) * ((p.W + tcb::MT - 1) / tcb::MT);
-    return align256((size_t)n_tiles * (tcb::RB + 4) * tcb::GW * sizeof(float));
+    const int rb = tcb::pick_rows(p);
+    const int64_t n_tiles = (int64_t)p.B * ((p.H + rb - 1) / rb) * ((p.W + tcb::MT - 1) / tcb::MT);
+    return align256((size_t)n_tiles * (rb + 4) * tcb::GW * sizeof(float));
 }
 
 int launch_tc_backward(const Problem &p, const float *grad, const float *cam, const float *proj, float *camera_grad,
