@@ -390,31 +390,40 @@ def run_b200(args):
     # ---- timed region 3: end to end through the C-ABI host entry point -------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_best = torch.empty(P, H, W).pin_memory()
-        h_disp = torch.empty(P, H, W, dtype=torch.int32).pin_memory()
-        h_grad = torch.empty(P, H, W).pin_memory()
+        # two sets of host result buffers: step i is submitted, then the results of step i-1 are waited for - the
+        # streaming use of the host entry point (copies of one step under the kernels of the other)
+        h_best2 = [torch.empty(P, H, W).pin_memory() for _ in range(2)]
+        h_disp2 = [torch.empty(P, H, W, dtype=torch.int32).pin_memory() for _ in range(2)]
+        h_grad2 = [torch.empty(P, H, W).pin_memory() for _ in range(2)]
 
-        def host_step():
-            binding.host_step(h_cam.data_ptr(), h_proj.data_ptr(), h_best.data_ptr(), h_disp.data_ptr(),
-                              h_grad.data_ptr(), cost.data_ptr(), grad_in.data_ptr(), P, H, W, D, k, flags)
+        def host_submit(i):
+            return binding.host_submit(h_cam.data_ptr(), h_proj.data_ptr(), h_best2[i & 1].data_ptr(), h_disp2[i & 1].data_ptr(),
+                                       h_grad2[i & 1].data_ptr(), cost.data_ptr(), grad_in.data_ptr(), P, H, W, D, k, flags)
 
-        for _ in range(3):
-            host_step()
+        for i in range(3):
+            binding.host_wait(host_submit(i))
         Ke = max(3, min(K, 20))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(Ke):
-            host_step()                                              # synchronous: returns with results on the host
+        prev = None
+        for i in range(Ke):
+            ticket = host_submit(i)                                  # H2D + forward + backward + D2H of step i enqueued
+            if prev is not None:
+                binding.host_wait(prev)                              # results of step i-1 are on the host
+            prev = ticket
+        binding.host_wait(prev)
         barrier()
         dt = time.perf_counter() - t0
+        h_best, h_grad = h_best2[(Ke - 1) & 1], h_grad2[(Ke - 1) & 1]
         te = torch.tensor([dt], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
         e2e = {"value": cells_job * Ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * P * pix * 4,
                "d2h_bytes_per_step": 3 * P * pix * 4, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
-               "api": "custma_host_step (include/custma_b200.h): pinned host images in, host best/disparity/"
-                      "camera_grad out; upstream gradient produced on the device"}
+               "api": "custma_host_submit / custma_host_wait (include/custma_b200.h; custma_host_step = both): pinned host "
+                      "images in, host best/disparity/camera_grad out every step, results of step i-1 awaited after "
+                      "step i is submitted; upstream gradient produced on the device"}
         # parity of the two paths on this very data (cheap sanity, outside the timed regions)
         same = bool(torch.equal(h_best.to(device), best) and torch.equal(h_grad.to(device), cam_grad))
         e2e["matches_device_path"] = same

@@ -35,6 +35,8 @@ SYMBOLS = (
     "custma_forward",
     "custma_backward",
     "custma_host_step",
+    "custma_host_submit",
+    "custma_host_wait",
     "custma_host_release",
 )
 
@@ -66,6 +68,11 @@ def _declare(lib):
     lib.custma_backward.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_host_step.restype = ctypes.c_int
     lib.custma_host_step.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32]
+    lib.custma_host_submit.restype = ctypes.c_int
+    lib.custma_host_submit.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32,
+                                       ctypes.POINTER(ctypes.c_uint64)]
+    lib.custma_host_wait.restype = ctypes.c_int
+    lib.custma_host_wait.argtypes = [ctypes.c_uint64]
     lib.custma_host_release.restype = ctypes.c_int
     lib.custma_host_release.argtypes = []
 
@@ -133,6 +140,21 @@ def host_step(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume
     rc = load().custma_host_step(h_camera, h_projector, h_best, h_index, h_camera_grad or None,
                                  cost_volume_dev or None, cost_volume_grad_dev or None, B, H, W, D, k, flags)
     check(rc, "custma_host_step")
+
+
+def host_submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev,
+                B, H, W, D, k, flags=0) -> int:
+    """custma_host_step without the final wait; returns the ticket to pass to host_wait."""
+    ticket = ctypes.c_uint64(0)
+    rc = load().custma_host_submit(h_camera, h_projector, h_best, h_index, h_camera_grad or None,
+                                   cost_volume_dev or None, cost_volume_grad_dev or None, B, H, W, D, k, flags,
+                                   ctypes.byref(ticket))
+    check(rc, "custma_host_submit")
+    return int(ticket.value)
+
+
+def host_wait(ticket: int = 0):
+    check(load().custma_host_wait(ticket), "custma_host_wait")
 
 
 def host_release():

@@ -11,6 +11,7 @@
 namespace custma {
 
 constexpr int kSlots = 2;
+constexpr int kTickets = 8;   // completion events kept for custma_host_wait
 constexpr size_t kChunkVolumeBytes = (size_t)3 << 30;  // per-slot cost-volume chunk kept in HBM
 
 struct Slot {
@@ -29,6 +30,9 @@ struct HostCtx {
     uint32_t flags = 0;
     bool with_volume = false;
     Slot slot[kSlots];
+    int next_slot = 0;                                 // slots keep rotating across calls, so consecutive steps overlap
+    uint64_t next_ticket = 1;
+    cudaEvent_t done[kTickets][kSlots] = {};           // done[t % kTickets][s]: slot s has delivered everything of ticket t
 };
 
 static HostCtx g_ctx;
@@ -46,22 +50,33 @@ static void release_locked() {
         cudaFree(s.ws);
         s = Slot();
     }
+    for (auto &row : g_ctx.done)
+        for (cudaEvent_t &e : row)
+            if (e) cudaEventDestroy(e);
     g_ctx = HostCtx();
 }
 
-static int ensure_ctx(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume) {
+// Pairs per pipelined chunk.  A synchronous step cuts the batch in two so that the copies of one half overlap the
+// kernels of the other (measured on 8 KITTI pairs: chunks of 1 / 2 / 4 / 8 pairs -> 3.54 / 3.24 / 3.03 / 3.38 ms per
+// step); a streamed step (custma_host_submit) overlaps with its neighbours instead and keeps the batch whole, so the
+// kernels' grids stay full.
+static int32_t pick_chunk(int32_t B, int32_t H, int32_t W, int32_t D, bool streamed) {
+    const int32_t C = D > 0 ? D : W;
+    const size_t pair_vol = (size_t)H * W * C * sizeof(float);
+    int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)B, kChunkVolumeBytes / std::max<size_t>(pair_vol, 1)));
+    if (!streamed && B >= kSlots) chunk = std::min(chunk, (B + kSlots - 1) / kSlots);
+    if (const char *e = getenv("CUSTMA_HOST_CHUNK")) {   // tuning knob
+        const int v = atoi(e);
+        if (v > 0) chunk = std::min<int32_t>(v, B);
+    }
+    return chunk;
+}
+
+static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume) {
     int dev = 0;
     CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
     const int32_t C = D > 0 ? D : W;
     const size_t pair_vol = (size_t)H * W * C * sizeof(float);
-    int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)B, kChunkVolumeBytes / std::max<size_t>(pair_vol, 1)));
-    // two chunks in flight: the copies of one overlap the kernels of the other; larger chunks keep the kernels' grids
-    // full (measured on 8 KITTI pairs: chunks of 1 / 2 / 4 / 8 pairs -> 3.54 / 3.24 / 3.03 / 3.38 ms per step)
-    if (B >= kSlots) chunk = std::min(chunk, (B + kSlots - 1) / kSlots);
-    if (const char *e = getenv("CUSTMA_HOST_CHUNK")) {   // tuning knob: pairs per pipelined chunk
-        const int v = atoi(e);
-        if (v > 0) chunk = std::min<int32_t>(chunk > 0 ? std::max(chunk, v) : v, B), chunk = std::min<int32_t>(v, B);
-    }
     if (g_ctx.live && g_ctx.device == dev && g_ctx.H == H && g_ctx.W == W && g_ctx.D == D && g_ctx.k == k &&
         g_ctx.flags == flags && g_ctx.chunk >= chunk && (g_ctx.with_volume || !need_volume))
         return CUSTMA_OK;
@@ -85,6 +100,8 @@ static int ensure_ctx(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uin
                               custma_backward_workspace_bytes(chunk, H, W, D, k, flags));
         CUSTMA_CUDA_CHECK(cudaMalloc(&s.ws, s.ws_bytes));
     }
+    for (auto &row : g_ctx.done)
+        for (cudaEvent_t &e : row) CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return CUSTMA_OK;
 }
 
@@ -100,9 +117,9 @@ int custma_host_release(void) {
     return CUSTMA_OK;
 }
 
-int custma_host_step(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
-                     float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
-                     int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+static int submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
+                  float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
+                  int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool streamed, uint64_t *ticket) {
     if (!h_camera || !h_projector || !h_best || !h_index)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "h_camera, h_projector, h_best and h_index must not be NULL");
     if ((cost_volume_grad_dev != nullptr) != (h_camera_grad != nullptr))
@@ -110,14 +127,13 @@ int custma_host_step(const float *h_camera, const float *h_projector, float *h_b
     if (B <= 0 || H <= 0 || W <= 0 || D < 0 || k < 1 || k > CUSTMA_MAX_KERNEL_SIZE)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "bad shape B=%d H=%d W=%d D=%d k=%d", B, H, W, D, k);
     std::lock_guard<std::mutex> lock(g_mutex);
-    int rc = ensure_ctx(B, H, W, D, k, flags, cost_volume_dev == nullptr);
+    const int32_t chunk = pick_chunk(B, H, W, D, streamed);
+    int rc = ensure_ctx(chunk, H, W, D, k, flags, cost_volume_dev == nullptr);
     if (rc) return rc;
     const int32_t C = D > 0 ? D : W;
     const size_t pix = (size_t)H * W;
-    const int32_t chunk = g_ctx.chunk;
-    int slot_i = 0;
-    for (int32_t b0 = 0; b0 < B; b0 += chunk, slot_i = (slot_i + 1) % kSlots) {
-        Slot &s = g_ctx.slot[slot_i];
+    for (int32_t b0 = 0; b0 < B; b0 += chunk, g_ctx.next_slot = (g_ctx.next_slot + 1) % kSlots) {
+        Slot &s = g_ctx.slot[g_ctx.next_slot];
         const int32_t nb = std::min(chunk, B - b0);
         const size_t img_bytes = (size_t)nb * pix * sizeof(float);
         // the slot's result buffers are free once the device->host copies of its previous chunk are done
@@ -143,11 +159,41 @@ int custma_host_step(const float *h_camera, const float *h_projector, float *h_b
         }
         CUSTMA_CUDA_CHECK(cudaEventRecord(s.d2h_done, s.d2h));
     }
-    for (Slot &s : g_ctx.slot) {
-        CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
-    }
+    const uint64_t t = g_ctx.next_ticket++;
+    for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventRecord(g_ctx.done[t % kTickets][i], g_ctx.slot[i].d2h));
+    if (ticket) *ticket = t;
     return CUSTMA_OK;
+}
+
+int custma_host_submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
+                       float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
+                       int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, uint64_t *ticket) {
+    return submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B, H, W, D,
+                  k, flags, true, ticket);
+}
+
+int custma_host_wait(uint64_t ticket) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_ctx.live) return CUSTMA_OK;
+    if (ticket == 0 || ticket >= g_ctx.next_ticket || ticket + kTickets <= g_ctx.next_ticket) {
+        // everything submitted so far (also for tickets whose events have been reused: later work completes later)
+        for (Slot &s : g_ctx.slot) {
+            CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+            CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
+        }
+        return CUSTMA_OK;
+    }
+    for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventSynchronize(g_ctx.done[ticket % kTickets][i]));
+    return CUSTMA_OK;
+}
+
+int custma_host_step(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
+                     float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
+                     int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    uint64_t t = 0;
+    const int rc = submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B,
+                          H, W, D, k, flags, false, &t);
+    return rc ? rc : custma_host_wait(0);
 }
 
 }  // extern "C"

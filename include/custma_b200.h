@@ -96,6 +96,14 @@ int custma_backward(const float *cost_volume_grad, const float *camera, const fl
 int custma_host_step(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
                      float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                      int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
+/* The same step without the final wait, for callers that stream batches: returns once everything is enqueued and
+ * stores a ticket; the host buffers of a ticket may be read (results) or rewritten (images) after
+ * custma_host_wait(ticket) - 0 waits for everything submitted so far.  Consecutive submits overlap: the copies of
+ * one step run under the kernels of the other, so keep two sets of host result buffers. */
+int custma_host_submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
+                       float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
+                       int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, uint64_t *ticket);
+int custma_host_wait(uint64_t ticket);
 /* Releases the device/stream resources custma_host_step caches between calls. */
 int custma_host_release(void);
 

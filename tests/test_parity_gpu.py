@@ -229,6 +229,29 @@ def test_runs_on_the_current_stream():
 # ---------------------------------------------------------------------------------------------------------------
 # error behaviour (custma/include/stereo_matching.hpp:20-29, custma/src/stereo_matching.cpp:23-24,52)
 # ---------------------------------------------------------------------------------------------------------------
+def test_host_submit_and_wait_stream_batches():
+    """custma_host_submit / custma_host_wait: two batches in flight give the same results as the device path."""
+    from custereomatching_b200 import binding
+    B, H, W, D, k = 3, 40, 200, 64, 5
+    sets = []
+    for i in range(2):
+        cam, proj = rand_pair(H, W, seed=50 + i, B=B)
+        g = np.random.RandomState(60 + i).randn(B, H, W, D).astype(np.float32)
+        sets.append((torch.from_numpy(cam).pin_memory(), torch.from_numpy(proj).pin_memory(), dev(g),
+                     torch.empty(B, H, W).pin_memory(), torch.empty(B, H, W, dtype=torch.int32).pin_memory(),
+                     torch.empty(B, H, W).pin_memory()))
+    tickets = [binding.host_submit(c.data_ptr(), p.data_ptr(), hb.data_ptr(), hi.data_ptr(), hg.data_ptr(), 0, g.data_ptr(),
+                                   B, H, W, D, k) for c, p, g, hb, hi, hg in sets]
+    assert tickets[1] == tickets[0] + 1
+    for t, (c, p, g, hb, hi, hg) in zip(tickets, sets):
+        binding.host_wait(t)
+        _, best, disp = cb.forward(c.cuda(), p.cuda(), D, k, want_cost=False, want_wta=True)
+        grad = cb.backward(g, c.cuda(), p.cuda(), k, D)
+        assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp) and torch.equal(hg.cuda(), grad)
+    binding.host_wait(0)
+    binding.host_release()
+
+
 def test_error_behaviour():
     cam = torch.rand(16, 16, device="cuda")
     with pytest.raises(RuntimeError, match="camera must be contiguous"):
