@@ -59,9 +59,12 @@ struct Smem {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// upper tf32 half, rounded to nearest (half away from zero) with two integer instructions - the tensor core itself would
-// truncate the low 13 mantissa bits; the residual v - hi then has at most 12 significant bits
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// Split for 3xTF32.  The tensor core reads only the upper 19 bits of an fp32 operand (it truncates), so both halves are
+// rounded to nearest here, with two integer instructions each: hi = rn_tf32(v), lo = rn_tf32(v - hi).  Left to the
+// hardware, the truncation of lo alone would cost 2^-22 per operand, several times the fp32 rounding of the reference.
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rn(v - hi); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 0) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | (uint64_t)(lbo_bytes >> 4) << 16 | (uint64_t)(sbo_bytes >> 4) << 32 | 1ull << 46 | (uint64_t)layout << 61;
 }
@@ -155,7 +158,7 @@ __device__ __forceinline__ float build_patch(const float *ring, int pitch, int y
     for (int c = 0; c < CHW; ++c) {
         float4 h, l;
         h.x = tf32_hi(v[4 * c]); h.y = tf32_hi(v[4 * c + 1]); h.z = tf32_hi(v[4 * c + 2]); h.w = tf32_hi(v[4 * c + 3]);
-        l.x = v[4 * c] - h.x; l.y = v[4 * c + 1] - h.y; l.z = v[4 * c + 2] - h.z; l.w = v[4 * c + 3] - h.w;
+        l.x = tf32_lo(v[4 * c], h.x); l.y = tf32_lo(v[4 * c + 1], h.y); l.z = tf32_lo(v[4 * c + 2], h.z); l.w = tf32_lo(v[4 * c + 3], h.w);
         *reinterpret_cast<float4 *>(hi[c][row]) = h;
         *reinterpret_cast<float4 *>(lo[c][row]) = l;
         if (hi2) {
@@ -334,11 +337,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                                 const float rs = rsqrtf(fmaf(e2, ee[k], kEps));
                                 float a = gg[k] * rs;                               // g / den; g is 0 where the cell does not exist
                                 if (p_first - i < 0) a = 0.f;                       // off-image projector column: constant cost
-                                const float cost = (__uint_as_float(dd[4 * g + k]) + kEps) * rs;
-                                bsum = fmaf(a * cost, ee[k] * rs, bsum);       // g * ey2 * (exy + eps) / den^3
+                                // what is left of a*mu - b (mu = exy / ex2, see the row epilogue): a * (exy - ex2*ey2) / den^2
+                                bsum = fmaf(a * rs * rs, fmaf(-e2, ee[k], __uint_as_float(dd[4 * g + k])), bsum);
                                 const float h = tf32_hi(a);
                                 ah[4 * g + k] = __float_as_uint(h);
-                                al[4 * g + k] = __float_as_uint(a - h);
+                                al[4 * g + k] = __float_as_uint(tf32_lo(a, h));
                             }
                         }
                         if (n == 16) { tmem_st16(t_ah + i0, ah); tmem_st16(t_al + i0, al); }
@@ -367,13 +370,25 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     tmem_ld16(g1, lane_addr + COL_G1);
                     tmem_ld16(g1 + 16, lane_addr + COL_G1 + 16);
                     tmem_wait_ld();
-                    const float Bs = (S.bs[0][L] + S.bs[1][L]) + (S.bs[2][L] + S.bs[3][L]);
-                    float pg[NTAP];
+                    // patch_grad = sum_p (a_p * pc_p - b_p * cc)   (reference kernel.cu:145-158).  With pc_p = mu_p * cc + pc_p^perp,
+                    // mu_p = <pc_p, cc> / <cc, cc> = exy_p / ex2, this is  sum_p a_p * pc_p^perp + (sum_p (a_p mu_p - b_p)) * cc,
+                    // i.e. G1 with its component along cc projected out, plus a term that is O(eps):
+                    //   a mu - b = a * eps * (exy - ex2*ey2) / (ex2 * den^2).
+                    // Subtracting Bs * cc from G1 directly would cancel two large sums on highly correlated images (and
+                    // expose the tensor core's truncating accumulation, which is mostly along G1 ~ cc); the projection
+                    // removes that component whatever its rounding was.
+                    const float csum = (S.bs[0][L] + S.bs[1][L]) + (S.bs[2][L] + S.bs[3][L]);
+                    const float e2x = S.ex2[L], inv_e2 = e2x > 0.f ? 1.f / e2x : 0.f;
+                    float cc[NTAP], dot = 0.f;
 #pragma unroll
                     for (int t = 0; t < NTAP; ++t) {
-                        const float cc = S.Ahi[t / 4][L][t % 4] + S.Alo[t / 4][L][t % 4];
-                        pg[t] = fmaf(-Bs, cc, __uint_as_float(g1[t]));
+                        cc[t] = S.Ahi[t / 4][L][t % 4] + S.Alo[t / 4][L][t % 4];
+                        dot = fmaf(__uint_as_float(g1[t]), cc[t], dot);
                     }
+                    const float coef = fmaf(kEps, csum, -dot) * inv_e2;
+                    float pg[NTAP];
+#pragma unroll
+                    for (int t = 0; t < NTAP; ++t) pg[t] = fmaf(coef, cc[t], __uint_as_float(g1[t]));
                     // scatter: tap (i, j) of camera column mp belongs to gradient pixel (r + i, mp + j); one column offset
                     // per phase, so no two threads touch the same element
 #pragma unroll

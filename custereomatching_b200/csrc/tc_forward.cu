@@ -61,7 +61,12 @@ struct Smem {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+// Split for 3xTF32.  The tensor core reads only the upper 19 bits of an fp32 operand (it truncates), so both halves are
+// rounded to nearest here, with two integer instructions each: hi = rn_tf32(v), lo = rn_tf32(v - hi).  Left to the
+// hardware, the truncation of lo alone would cost 2^-22 per operand, several times the fp32 rounding of the reference.
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_rn(v - hi); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // start address, leading / stride byte offsets (all >> 4), descriptor version 1, no swizzle
     return (uint64_t)((addr & 0x3ffffu) >> 4) | (uint64_t)(lbo_bytes >> 4) << 16 | (uint64_t)(sbo_bytes >> 4) << 32 | 1ull << 46;
@@ -136,7 +141,7 @@ __device__ __forceinline__ float build_patch(const float *ring, int pitch, int y
     for (int c = 0; c < G::CHW; ++c) {
         float4 h, l;
         h.x = tf32_hi(v[4 * c]); h.y = tf32_hi(v[4 * c + 1]); h.z = tf32_hi(v[4 * c + 2]); h.w = tf32_hi(v[4 * c + 3]);
-        l.x = v[4 * c] - h.x; l.y = v[4 * c + 1] - h.y; l.z = v[4 * c + 2] - h.z; l.w = v[4 * c + 3] - h.w;
+        l.x = tf32_lo(v[4 * c], h.x); l.y = tf32_lo(v[4 * c + 1], h.y); l.z = tf32_lo(v[4 * c + 2], h.z); l.w = tf32_lo(v[4 * c + 3], h.w);
         *reinterpret_cast<float4 *>(hi[c][row]) = h;
         *reinterpret_cast<float4 *>(lo[c][row]) = l;
     }
