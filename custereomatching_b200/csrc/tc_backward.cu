@@ -282,6 +282,26 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 float bsum = 0.f;
                 for (int blk = 0; blk < nblk; ++blk, ++J) {
                     worker_sync();   // every worker is done with the previous job's stage / ey2; its GEMM 1 has been waited for
+                    // gradient tile of this job -> stage (same slots as the forward's write-out; zeros where no cell exists),
+                    // as 16-byte cp.async so that it is in flight during the operand build
+                    if (tid < 18 * NQ) {
+                        const int g4 = tid % NQ, row0 = tid / NQ;
+                        const int s_off = blk * PW - (MT + 3) + 4 * g4;
+                        const float *gbase = grad + ((int64_t)b * H + y) * W * D;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int Lr = row0 + 18 * k;
+                            const int qL = Lr >> 5, mL = 4 * (Lr & 31) + qL, xr = x0 + mL;
+                            const int s = mL + s_off + ((3 - qL) & 3);
+                            if (Lr < MT) {
+                                const bool live = xr < W && (unsigned)s < (unsigned)D;
+                                const float *src = live ? gbase + (int64_t)xr * D + s : gbase;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&S.stage[Lr][4 * g4])), "l"(src),
+                                             "r"(live ? 16 : 0) : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                     const int nA = blk == 0 ? MT : 0;
                     if (tid < nA) {
                         const int col0 = 4 * (tid & 31) + (tid >> 5);
@@ -297,24 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     fence_before();
                     bar_arrive(smem_u32(&S.ops1_bar));
-                    // (the tensor core now runs MMA1; the gradient tile is fetched meanwhile)
-                    // gradient tile of this job -> stage (same slots as the forward's write-out), zeros where no cell exists
-                    if (tid < 18 * NQ) {
-                        const int g4 = tid % NQ, row0 = tid / NQ;
-                        const int s_off = blk * PW - (MT + 3) + 4 * g4;
-                        const float *gbase = grad + ((int64_t)b * H + y) * W * D;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int Lr = row0 + 18 * k;
-                            const int qL = Lr >> 5, mL = 4 * (Lr & 31) + qL, xr = x0 + mL;
-                            const int s = mL + s_off + ((3 - qL) & 3);
-                            if (Lr < MT) {
-                                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (xr < W && (unsigned)s < (unsigned)D) g = __ldcs(reinterpret_cast<const float4 *>(gbase + (int64_t)xr * D + s));
-                                *reinterpret_cast<float4 *>(&S.stage[Lr][4 * g4]) = g;
-                            }
-                        }
-                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                     worker_sync();                                   // stage and ey2 / ex2 are complete
                     bar_wait(smem_u32(&S.mma1_bar), J & 1);   // GEMM 1 of this job - and, the tensor core running in order, GEMM 2 of the
                     fence_after();                           // previous one: A_hi / A_lo may be overwritten
