@@ -6,19 +6,27 @@
 // A * pc[p][tap] - B * cc[x][tap] to the k x k camera pixels of the window with atomicAdd (:150-158).  Summed over the
 // projector columns of one camera pixel that is again a dense contraction:
 //     MMA1   D1[128 x 128]  = CC * PC^T                                 exy, as in the forward (3xTF32, fp32 in TMEM)
-//     epi1   a = g * rsqrt(ex2 * ey2 + eps),  Bs += a * cost * ey2 * rsqrt(...)        per camera column, fp32
-//            a -> two tf32 halves written back into TMEM (the high half over D1 in place)
+//     epi1   a = g * rsqrt(ex2 * ey2 + eps)  -> two tf32 halves written back into TMEM (tcgen05.st),
+//            csum += a * (exy - ex2 * ey2) / den^2                       per camera column, fp32 (see "row")
 //     MMA2   G1[128 x 32]  += A_hi * PC_hi + A_hi * PC_lo + A_lo * PC_hi          A operand from TMEM, PC MN-major
-//     row    patch_grad[x][tap] = G1[x][tap] - Bs[x] * cc[x][tap], scattered into the tile's gradient image in shared
-//            memory (one window column per phase: no two threads touch one element, no atomics)
-// Each tile (128 camera columns x 16 rows) writes its gradient image with a window-radius halo to a scratch tile;
-// tc_backward_finalize_kernel adds the overlapping halos in a fixed order: deterministic, like the sliding path.
+//     row    patch_grad[x] = G1[x] - (<G1[x], cc[x]> / ex2) * cc[x] + (eps * csum / ex2) * cc[x]
+//            (sum_p (a pc - b cc) with the component along cc taken analytically instead of as a difference of two
+//            large sums), scattered into the tile's gradient image in shared memory, one window column per phase:
+//            no two threads touch one element, no atomics
+// Each tile (128 camera columns x up to 16 rows) writes its gradient image with a window-radius halo to a scratch
+// tile; tc_backward_finalize_kernel adds the overlapping halos in a fixed order: deterministic, like the sliding path.
+//
+// Pipeline of a job j (workers = 16 warps, one more warp issues the MMAs): barrier | cp.async of the upstream-gradient
+// tile into the stage | build CC (first job of a row) and PC | arrive -> MMA1(j) | wait for the copies, barrier, wait
+// for MMA1(j) (which, the tensor core running in order, also means MMA2(j-1) is done) | epi1 | arrive -> MMA2(j), which
+// runs under the build of job j+1 (D1, A_hi, A_lo and G1 have their own TMEM columns; the MN-major PC copy alternates
+// between two buffers).
 //
 // PC lives in shared memory twice: K-major without swizzle for MMA1 (as in tc_forward.cu) and as rows of 32 taps with
 // 32-byte units XOR (row % 4) for MMA2 - the only MN-major layout the tensor core accepts for 32-bit operands
 // (UMMA layout type 1, "128B swizzle with 32-byte base"; tools/tc_mma_probe.cu: every other MN-major layout made the
-// MMA a no-op).  Thread / TMEM-lane / column mapping, the image ring and the job pipeline are those of tc_forward.cu,
-// with 112 projector columns per job so that both copies fit.
+// MMA a no-op).  Thread / TMEM-lane / column mapping and the image ring are those of tc_forward.cu, with 112 projector
+// columns per job so that everything fits in 226 KB of shared memory.
 #include <algorithm>
 
 #include "sliding_common.cuh"
