@@ -300,7 +300,8 @@ def run_b200(args):
     results = torch.empty(2, P, H, W, device=device)
     best = results[0]
     disp = results[1].view(torch.int32)
-    cam_grad = torch.empty(P, H, W, device=device)
+    cam_grad2 = [torch.empty(P, H, W, device=device) for _ in range(2)]   # two buffers: the gather of one step's gradient
+    cam_grad = cam_grad2[0]                                               # runs under the next step's forward
     ws_bytes = max(binding.forward_workspace_bytes(P, H, W, D, k, flags),
                    binding.backward_workspace_bytes(P, H, W, D, k, flags))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
@@ -314,17 +315,31 @@ def run_b200(args):
         binding.forward(cam.data_ptr(), proj.data_ptr(), cost.data_ptr(), best.data_ptr(), disp.data_ptr(),
                         P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
 
-    def bwd():
-        binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(),
+    def bwd(out=None):
+        binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), (cam_grad if out is None else out).data_ptr(),
                          P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
 
+    state = {"i": 0, "grad_pending": None}
+
     def step():
+        # results only cross GPUs: 3 * P*H*W*4 bytes per rank; the volume never leaves its GPU.  Both gathers are
+        # asynchronous (NCCL's own stream): best / disparity leave under this step's backward, the camera gradient
+        # under the NEXT step's forward; finish_steps() waits for the last one inside the timed region.
         fwd()
         pending = dist.all_gather_into_tensor(gathered, results, async_op=True) if world > 1 else None
-        bwd()   # results only cross GPUs: 3 * P*H*W*4 bytes per rank; the volume never leaves its GPU
+        if state["grad_pending"] is not None:
+            state["grad_pending"].wait()
+        out = cam_grad2[state["i"] & 1]
+        state["i"] += 1
+        bwd(out)
         if world > 1:
-            dist.all_gather_into_tensor(gathered_grad, cam_grad)
+            state["grad_pending"] = dist.all_gather_into_tensor(gathered_grad, out, async_op=True)
             pending.wait()
+
+    def finish_steps():
+        if state["grad_pending"] is not None:
+            state["grad_pending"].wait()
+            state["grad_pending"] = None
 
     def barrier():
         if world > 1:
@@ -333,6 +348,7 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    finish_steps()
     barrier()
 
     # ---- timed region 1: whole step, device-resident inputs ------------------------------------------------------
@@ -344,6 +360,7 @@ def run_b200(args):
         ev[0].record(stream)
         for _ in range(K):
             step()
+        finish_steps()
         ev[1].record(stream)
         barrier()
     launches = (binding.launch_count() - launches0) // K
