@@ -201,12 +201,17 @@ __global__ void __launch_bounds__(256)
     const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RBH - L.r);
     const int x0 = max(0, wt * L.WTC - L.r), x1 = min(p.W, wt * L.WTC - L.r + L.WTC + L.K - 1);
     float vmax = -INFINITY, vmin = INFINITY;
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0 + lane; x < x1; x += 32) {
-            const float v = __ldg(plane + (int64_t)y * p.W + x);
-            vmax = fmaxf(vmax, v);
-            vmin = fminf(vmin, v);
-        }
+    // flattened over the tile's pixels and unrolled: eight independent loads in flight per lane (a row-by-row loop had
+    // one, and the first touch of the camera image comes from DRAM: 36 us per call instead of a few)
+    const int w = x1 - x0, n = w * (y1 - y0);
+    const float *origin = plane + (int64_t)y0 * p.W + x0;
+#pragma unroll 8
+    for (int i = lane; i < n; i += 32) {
+        const int yy = i / w, xx = i - yy * w;
+        const float v = __ldg(origin + (int64_t)yy * p.W + xx);
+        vmax = fmaxf(vmax, v);
+        vmin = fminf(vmin, v);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
