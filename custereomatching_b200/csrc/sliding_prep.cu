@@ -189,37 +189,43 @@ __global__ void __launch_bounds__(256)
 }
 
 // camera pivot per (pair, band, column tile): mid-range of the in-image pixels of the tile's footprint (its columns plus
-// the window halo, the band's rows plus halo).  One warp per tile.
-__global__ void __launch_bounds__(256)
-    camera_tile_pivot_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, float *__restrict__ campiv) {
-    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
-    if (tile >= ntiles) return;
-    const int lane = threadIdx.x & 31;
-    const int wt = (int)(tile % L.n_wtiles), nb = (int)((tile / L.n_wtiles) % L.NB), b = (int)(tile / ((int64_t)L.n_wtiles * L.NB));
+// the window halo, the band's rows plus halo).  A block takes a run of whole tiles: one thread per image column marches
+// down the band's rows (coalesced, each pixel read once per band), the per-column extrema go to shared memory and one
+// thread per tile combines its columns.  (One warp per tile, each reading its own 20-column footprint, was 25-36 us per
+// call: latency-bound and uncoalesced.)
+constexpr int kPivotThreads = 256;
+__global__ void __launch_bounds__(kPivotThreads)
+    camera_tile_pivot_kernel(Problem p, SlidingLayout L, int tiles_per_block, const float *__restrict__ cam,
+                             float *__restrict__ campiv) {
+    __shared__ float cmax[kPivotThreads], cmin[kPivotThreads];
+    const int nb = blockIdx.y, b = blockIdx.z, wt0 = blockIdx.x * tiles_per_block;
     const float *plane = cam + (int64_t)b * p.H * p.W;
     const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RBH - L.r);
-    const int x0 = max(0, wt * L.WTC - L.r), x1 = min(p.W, wt * L.WTC - L.r + L.WTC + L.K - 1);
+    const int xb = wt0 * L.WTC - L.r;                                   // image column of thread 0
+    const int ncols = min(tiles_per_block, L.n_wtiles - wt0) * L.WTC + L.K - 1;
+    const int x = xb + (int)threadIdx.x;
     float vmax = -INFINITY, vmin = INFINITY;
-    // flattened over the tile's pixels and unrolled: eight independent loads in flight per lane (a row-by-row loop had
-    // one, and the first touch of the camera image comes from DRAM: 36 us per call instead of a few)
-    const int w = x1 - x0, n = w * (y1 - y0);
-    const float *origin = plane + (int64_t)y0 * p.W + x0;
+    if ((int)threadIdx.x < ncols && x >= 0 && x < p.W) {
+        const float *col = plane + x;
 #pragma unroll 8
-    for (int i = lane; i < n; i += 32) {
-        const int yy = i / w, xx = i - yy * w;
-        const float v = __ldg(origin + (int64_t)yy * p.W + xx);
-        vmax = fmaxf(vmax, v);
-        vmin = fminf(vmin, v);
+        for (int y = y0; y < y1; ++y) {
+            const float v = __ldg(col + (int64_t)y * p.W);
+            vmax = fmaxf(vmax, v);
+            vmin = fminf(vmin, v);
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    }
-    if (lane == 0) {
-        const float pv = 0.5f * (vmax + vmin);
-        campiv[tile] = (vmax >= vmin && isfinite(pv)) ? pv : 0.f;
+    cmax[threadIdx.x] = vmax;
+    cmin[threadIdx.x] = vmin;
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < tiles_per_block && wt0 + t < L.n_wtiles) {
+        float hi = -INFINITY, lo = INFINITY;
+        for (int c = t * L.WTC; c < t * L.WTC + L.WTC + L.K - 1; ++c) {
+            hi = fmaxf(hi, cmax[c]);
+            lo = fminf(lo, cmin[c]);
+        }
+        const float pv = 0.5f * (hi + lo);
+        campiv[((int64_t)b * L.NB + nb) * L.n_wtiles + wt0 + t] = (hi >= lo && isfinite(pv)) ? pv : 0.f;
     }
 }
 
@@ -396,8 +402,9 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
         dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, p.B);
         band_minmax_kernel<<<grid, 256, 0, stream>>>(p, L, proj, minmax);
         CUSTMA_LAUNCH_CHECK("band_minmax_kernel");
-        const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
-        camera_tile_pivot_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, stream>>>(p, L, cam, campiv);
+        const int tiles_per_block = std::max(1, (kPivotThreads - (L.K - 1)) / L.WTC);
+        dim3 pgrid((L.n_wtiles + tiles_per_block - 1) / tiles_per_block, L.NB, p.B);
+        camera_tile_pivot_kernel<<<pgrid, kPivotThreads, 0, stream>>>(p, L, tiles_per_block, cam, campiv);
         CUSTMA_LAUNCH_CHECK("camera_tile_pivot_kernel");
     }
     {
