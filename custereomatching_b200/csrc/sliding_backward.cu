@@ -503,12 +503,32 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
+    // ---- horizontal k-sums of the staged rows, once per (row, column) instead of once per pixel that uses them:
+    // R1 = sum_j q1, R2A / R2B = the part of sum_j q2 whose cells lie in column tile wtA / wtA - 1 (same j order as the
+    // per-pixel loop they replace, so the result is bit-identical)
+    __shared__ float R1[SH][kFinTX], R2A[SH][kFinTX], R2B[SH][kFinTX];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+        const int hh = threadIdx.y + ph * kFinTY;
+        if (hh >= SH) continue;
+        float s1 = 0.f, s2A = 0.f, s2B = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            s1 += q1[hh][threadIdx.x + K - 1 - j];
+            if (j <= rx) s2A += q2[hh][threadIdx.x + K - 1 - j];
+            else s2B += q2[hh][threadIdx.x + K - 1 - j];
+        }
+        R1[hh][threadIdx.x] = s1;
+        R2A[hh][threadIdx.x] = s2A;
+        R2B[hh][threadIdx.x] = s2B;
+    }
+    __syncthreads();
     if (x >= p.W || y >= p.H) return;
     // ---- T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does
     // the previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts of
     // the images are never read.
     const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
-    const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
     float acc = 0.f;
     {
         const int off = (y + r) * BL.Wp + (x + r);
@@ -526,25 +546,29 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
         }
     }
     // ---- per-pixel terms: cell rows h = y + r - i (band nbA unless i > ry), cell columns w = x + r - j (column tile wtA
-    // unless j > rx); cam' and A of a cell are relative to the pivot of the cell's own tile
+    // unless j > rx); cam' of the target pixel relative to the pivot of the cell's own tile: two bands x two tiles
+    float cvA0 = 0.f, cvB0 = 0.f, cvA1 = 0.f, cvB1 = 0.f;
+    {
+        const int cA = wtA * L.seg_cam + (x - (wtA * L.WTC - r)), cB = (wtA - 1) * L.seg_cam + (x - ((wtA - 1) * L.WTC - r));
+        if (nbA < L.NB) {
+            const float *crow = camP + (nbA * L.RBH + ry) * L.cam_pitch;
+            cvA0 = wtA < L.n_wtiles ? crow[cA] : 0.f;
+            cvB0 = wtA > 0 ? crow[cB] : 0.f;
+        }
+        if (nbA >= 1 && ry < K - 1) {
+            const float *crow = camP + ((nbA - 1) * L.RBH + ry + L.RB) * L.cam_pitch;
+            cvA1 = wtA < L.n_wtiles ? crow[cA] : 0.f;
+            cvB1 = wtA > 0 ? crow[cB] : 0.f;
+        }
+    }
     float sub = 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const int h = y - i + r;
         if (h < 0 || h >= p.H) continue;
-        const int nb = i <= ry ? nbA : nbA - 1;
-        const float *crow = camP + (nb * L.RBH + (y - (nb * L.RB - r))) * L.cam_pitch;
-        const float cvA = wtA < L.n_wtiles ? crow[wtA * L.seg_cam + (x - (wtA * L.WTC - r))] : 0.f;
-        const float cvB = wtA > 0 ? crow[(wtA - 1) * L.seg_cam + (x - ((wtA - 1) * L.WTC - r))] : 0.f;
+        const bool own = i <= ry;
         const int hh = threadIdx.y + K - 1 - i;
-        float s1 = 0.f, s2A = 0.f, s2B = 0.f;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            s1 += q1[hh][threadIdx.x + K - 1 - j];
-            if (j <= rx) s2A += q2[hh][threadIdx.x + K - 1 - j];
-            else s2B += q2[hh][threadIdx.x + K - 1 - j];
-        }
-        sub += fmaf(cvA, s2A, fmaf(cvB, s2B, s1));
+        sub += fmaf(own ? cvA0 : cvA1, R2A[hh][threadIdx.x], fmaf(own ? cvB0 : cvB1, R2B[hh][threadIdx.x], R1[hh][threadIdx.x]));
     }
     acc -= sub;
     if (flagged_near) {   // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178 as a gather)
