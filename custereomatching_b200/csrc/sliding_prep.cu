@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256)
 // Conditioning of a window: rho = n * max|v|^2 / e2 (how much larger the raw sums are than what survives the
 // cancellation); the worst rho per block of 16 columns feeds the tile verdict.  rho = 0 for an exactly constant window
 // of pivoted zeros, infinite for any other flat window.
-constexpr int kStatRows = 16;   // output rows per thread of band_stats_kernel
+constexpr int kStatRows = 24;   // output rows per thread of band_stats_kernel (+ k-1 warm-up rows)
 
 template <int K>
 __global__ void __launch_bounds__(128)
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128)
             // neutral values elsewhere: they only ever meet masked cells
             o1[(int64_t)hr * pitch] = ok ? (img ? sum : sum * inv_n) : 0.f;
             o2[(int64_t)hr * pitch] = ok ? e2 : 1.f;
-            if (ok && sm > 0.f) rho = fmaxf(rho, (float)(K * K) * sm * sm / e2);   // e2 == 0 -> inf
+            if (ok && sm > 0.f) rho = fmaxf(rho, __fdividef((float)(K * K) * sm * sm, e2));   // e2 == 0 -> inf; a verdict, not a result
         }
     }
     // non-negative floats (and +inf) order like unsigned integers
