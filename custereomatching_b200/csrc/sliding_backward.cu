@@ -438,10 +438,10 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
 
 // camera_grad[y,x] = sum of the T1 tiles that cover (y,x) - sum over the k x k cells (h,w) whose window holds (y,x) of
 // ( Am[h,w] + Bs[h,w] * (cam'[y,x] - A[h,w]) ), cam' and A relative to the pivot of the band of row h.  Written as
-// sum_h ( sum_w q1[h,w] + cam'_h[y,x] * sum_w q2[h,w] ) with q1 = Am - Bs*A, q2 = Bs staged per 32x8 pixel block in
+// sum_h ( sum_w q1[h,w] + cam'_h[y,x] * sum_w q2[h,w] ) with q1 = Am - Bs*A, q2 = Bs staged per 32x32 pixel block (four pixels per thread) in
 // shared memory.  Fixed summation order; out-of-image cells do not exist, out-of-image targets are never computed
 // (reference :177).  Cells of flagged chunks arrive as ready-made patch gradients (sliding_fallback.cu).
-constexpr int kFinTX = 32, kFinTY = 8;
+constexpr int kFinTX = 32, kFinTY = 8, kFinRows = 32;   // thread block, pixel rows per block (kFinRows / kFinTY per thread)
 
 // x / d for a block-local x: d-aligned base known, a short loop instead of an integer division
 __device__ __forceinline__ int div_near(int x, int d, int q0) {   // q0 * d <= x required
@@ -455,10 +455,12 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad, const uint32_t tc_threshold) {
     if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
-    constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinTY + K - 1;
-    static_assert(SH <= 2 * kFinTY && SW <= 2 * kFinTX, "two passes of the thread block cover the staged cells");
+    constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinRows + K - 1;
+    // q1 = Am - Bs*A and q2 = Bs of the cells around the block; R* = their horizontal k-sums per (cell row, pixel column)
     __shared__ float q1[SH][SW + 1], q2[SH][SW + 1];
-    const int x0 = blockIdx.x * kFinTX, y0 = blockIdx.y * kFinTY, b = blockIdx.z;
+    __shared__ float R1[SH][kFinTX], R2A[SH][kFinTX], R2B[SH][kFinTX];
+    const int x0 = blockIdx.x * kFinTX, y0 = blockIdx.y * kFinRows, b = blockIdx.z;
+    const int tid = threadIdx.y * kFinTX + threadIdx.x;
     // block-uniform bases (64-bit once); per-thread offsets stay 32-bit (every image of one pair is < 2^31 floats)
     const int chunk_stride = L.NB * L.RB * L.cs_pitch;                      // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
     const float *Am = (const float *)(ws + BL.off_Am) + (int64_t)b * L.n_chunks * chunk_stride;
@@ -472,46 +474,34 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     const int nb_lo = max(y0 - back, 0) / L.RB, wt_lo = max(x0 - back, 0) / L.WTC;
     int flagged_near = 0;
     {
-        const int nb_hi = min((y0 + kFinTY - 1 + r) / L.RB, L.NB - 1), wt_hi = min((x0 + kFinTX - 1 + r) / L.WTC, L.n_wtiles - 1);
+        const int nb_hi = min((y0 + kFinRows - 1 + r) / L.RB, L.NB - 1), wt_hi = min((x0 + kFinTX - 1 + r) / L.WTC, L.n_wtiles - 1);
         for (int nb = nb_lo; nb <= nb_hi; ++nb)
             for (int wt = wt_lo; wt <= wt_hi; ++wt) flagged_near |= tileany[nb * L.n_wtiles + wt];
     }
     // ---- stage q1 = Am - Bs * A and q2 = Bs (summed over the chunks; flagged tiles hold zeros) for the cells around
-#pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-        const int hh = threadIdx.y + ph * kFinTY, h = y0 - back + hh;
-        if (hh >= SH) continue;
-        const bool h_ok = h >= 0 && h < p.H;
-        const int row = (h_ok ? h : 0) * L.cs_pitch;
-#pragma unroll
-        for (int pw = 0; pw < 2; ++pw) {
-            const int ww = threadIdx.x + pw * kFinTX, w = x0 - back + ww;
-            if (ww >= SW) continue;
-            float v1 = 0.f, v2 = 0.f;
-            if (h_ok && w >= 0 && w < p.W) {
-                float am = 0.f, bs = 0.f;
-                for (int ch = 0; ch < L.n_chunks; ++ch) {
-                    am += Am[row + w + ch * chunk_stride];
-                    bs += Bs[row + w + ch * chunk_stride];
-                }
-                v1 = fmaf(-bs, A[row + w], am);
-                v2 = bs;
+    for (int e = tid; e < SH * SW; e += kFinTX * kFinTY) {
+        const int hh = e / SW, ww = e - hh * SW;
+        const int h = y0 - back + hh, w = x0 - back + ww;
+        float v1 = 0.f, v2 = 0.f;
+        if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
+            const int at = h * L.cs_pitch + w;
+            float am = 0.f, bs = 0.f;
+            for (int ch = 0; ch < L.n_chunks; ++ch) {
+                am += Am[at + ch * chunk_stride];
+                bs += Bs[at + ch * chunk_stride];
             }
-            q1[hh][ww] = v1;
-            q2[hh][ww] = v2;
+            v1 = fmaf(-bs, A[at], am);
+            v2 = bs;
         }
+        q1[hh][ww] = v1;
+        q2[hh][ww] = v2;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int x = x0 + threadIdx.x;
     const int wtA = div_near(x + r, L.WTC, wt_lo), rx = x + r - wtA * L.WTC;
-    // ---- horizontal k-sums of the staged rows, once per (row, column) instead of once per pixel that uses them:
-    // R1 = sum_j q1, R2A / R2B = the part of sum_j q2 whose cells lie in column tile wtA / wtA - 1 (same j order as the
-    // per-pixel loop they replace, so the result is bit-identical)
-    __shared__ float R1[SH][kFinTX], R2A[SH][kFinTX], R2B[SH][kFinTX];
-#pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-        const int hh = threadIdx.y + ph * kFinTY;
-        if (hh >= SH) continue;
+    // ---- horizontal k-sums of the staged rows, once per (cell row, pixel column): R1 = sum_j q1, R2A / R2B = the part
+    // of sum_j q2 whose cells lie in column tile wtA / wtA - 1
+    for (int hh = threadIdx.y; hh < SH; hh += kFinTY) {
         float s1 = 0.f, s2A = 0.f, s2B = 0.f;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -524,68 +514,74 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
         R2B[hh][threadIdx.x] = s2B;
     }
     __syncthreads();
-    if (x >= p.W || y >= p.H) return;
-    // ---- T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does
-    // the previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts of
-    // the images are never read.
-    const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
-    float acc = 0.f;
-    {
-        const int off = (y + r) * BL.Wp + (x + r);
+    if (x >= p.W) return;
+    // pivoted camera value of the target pixel in the copies of column tiles wtA and wtA - 1 (offsets within a copy row)
+    const int cA = wtA * L.seg_cam + (x - (wtA * L.WTC - r)), cB = (wtA - 1) * L.seg_cam + (x - ((wtA - 1) * L.WTC - r));
+    const bool hasA = wtA < L.n_wtiles, hasB = wtA > 0;
+    const bool two_x = hasB && rx < K - 1;                                   // T1: the previous column tile's image too
+#pragma unroll 1
+    for (int m = 0; m < kFinRows / kFinTY; ++m) {
+        const int ty = threadIdx.y + m * kFinTY, y = y0 + ty;
+        if (y >= p.H) break;
+        // ---- T1 images: cell row y + r belongs to band nbA, whose image (parity nbA & 1) holds this target row; so does
+        // the previous band's while y + r is inside the k-1 rows the two bands share.  Same along x.  Unwritten parts
+        // of the images are never read.
+        const int nbA = div_near(y + r, L.RB, nb_lo), ry = y + r - nbA * L.RB;
+        float acc = 0.f;
+        {
+            const int off = (y + r) * BL.Wp + (x + r);
 #pragma unroll
-        for (int db = 0; db < 2; ++db) {
-            const int nb = nbA - db;
-            if (nb < 0 || nb >= L.NB || (db && ry >= K - 1)) continue;
+            for (int db = 0; db < 2; ++db) {
+                const int nb = nbA - db;
+                if (nb < 0 || nb >= L.NB || (db && ry >= K - 1)) continue;
 #pragma unroll
-            for (int dw = 0; dw < 2; ++dw) {
-                const int wt = wtA - dw;
-                if (wt < 0 || wt >= L.n_wtiles || (dw && rx >= K - 1)) continue;
-                const float *src = T1 + ((nb & 1) * 2 + (wt & 1)) * img + off;
-                for (int ch = 0; ch < L.n_chunks; ++ch) acc += src[ch * 4 * img];
+                for (int dw = 0; dw < 2; ++dw) {
+                    const int wt = wtA - dw;
+                    if (dw ? !two_x : !hasA) continue;
+                    const float *src = T1 + ((nb & 1) * 2 + (wt & 1)) * img + off;
+                    for (int ch = 0; ch < L.n_chunks; ++ch) acc += src[ch * 4 * img];
+                }
             }
         }
-    }
-    // ---- per-pixel terms: cell rows h = y + r - i (band nbA unless i > ry), cell columns w = x + r - j (column tile wtA
-    // unless j > rx); cam' of the target pixel relative to the pivot of the cell's own tile: two bands x two tiles
-    float cvA0 = 0.f, cvB0 = 0.f, cvA1 = 0.f, cvB1 = 0.f;
-    {
-        const int cA = wtA * L.seg_cam + (x - (wtA * L.WTC - r)), cB = (wtA - 1) * L.seg_cam + (x - ((wtA - 1) * L.WTC - r));
+        // ---- per-pixel terms: cell rows h = y + r - i (band nbA unless i > ry), cell columns w = x + r - j (column tile
+        // wtA unless j > rx); cam' of the target pixel relative to the pivot of the cell's own tile: two bands x two tiles
+        float cvA0 = 0.f, cvB0 = 0.f, cvA1 = 0.f, cvB1 = 0.f;
         if (nbA < L.NB) {
             const float *crow = camP + (nbA * L.RBH + ry) * L.cam_pitch;
-            cvA0 = wtA < L.n_wtiles ? crow[cA] : 0.f;
-            cvB0 = wtA > 0 ? crow[cB] : 0.f;
+            cvA0 = hasA ? crow[cA] : 0.f;
+            cvB0 = hasB ? crow[cB] : 0.f;
         }
         if (nbA >= 1 && ry < K - 1) {
             const float *crow = camP + ((nbA - 1) * L.RBH + ry + L.RB) * L.cam_pitch;
-            cvA1 = wtA < L.n_wtiles ? crow[cA] : 0.f;
-            cvB1 = wtA > 0 ? crow[cB] : 0.f;
+            cvA1 = hasA ? crow[cA] : 0.f;
+            cvB1 = hasB ? crow[cB] : 0.f;
         }
-    }
-    float sub = 0.f;
+        float sub = 0.f;
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const int h = y - i + r;
-        if (h < 0 || h >= p.H) continue;
-        const bool own = i <= ry;
-        const int hh = threadIdx.y + K - 1 - i;
-        sub += fmaf(own ? cvA0 : cvA1, R2A[hh][threadIdx.x], fmaf(own ? cvB0 : cvB1, R2B[hh][threadIdx.x], R1[hh][threadIdx.x]));
-    }
-    acc -= sub;
-    if (flagged_near) {   // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178 as a gather)
-        const float *patch = (const float *)(ws + BL.off_patch) + (int64_t)b * p.H * p.W * (K * K);
         for (int i = 0; i < K; ++i) {
             const int h = y - i + r;
             if (h < 0 || h >= p.H) continue;
-            const int nb = i <= ry ? nbA : nbA - 1;
-            for (int j = 0; j < K; ++j) {
-                const int w = x - j + r;
-                if (w < 0 || w >= p.W) continue;
-                if (tileany[nb * L.n_wtiles + (j <= rx ? wtA : wtA - 1)])
-                    acc += patch[((int64_t)h * p.W + w) * (K * K) + i * K + j];
+            const bool own = i <= ry;
+            const int hh = ty + K - 1 - i;
+            sub += fmaf(own ? cvA0 : cvA1, R2A[hh][threadIdx.x], fmaf(own ? cvB0 : cvB1, R2B[hh][threadIdx.x], R1[hh][threadIdx.x]));
+        }
+        acc -= sub;
+        if (flagged_near) {   // cells of flagged chunks arrive as ready-made patch gradients (reference :172-178 as a gather)
+            const float *patch = (const float *)(ws + BL.off_patch) + (int64_t)b * p.H * p.W * (K * K);
+            for (int i = 0; i < K; ++i) {
+                const int h = y - i + r;
+                if (h < 0 || h >= p.H) continue;
+                const int nb = i <= ry ? nbA : nbA - 1;
+                for (int j = 0; j < K; ++j) {
+                    const int w = x - j + r;
+                    if (w < 0 || w >= p.W) continue;
+                    if (tileany[nb * L.n_wtiles + (j <= rx ? wtA : wtA - 1)])
+                        acc += patch[((int64_t)h * p.W + w) * (K * K) + i * K + j];
+                }
             }
         }
+        camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc;
     }
-    camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc;
 }
 
 template <int K, int NU, int WG>
@@ -654,7 +650,7 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, thr, stream) : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, thr, stream);
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
-    const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinTY - 1) / kFinTY, p.B), fblock(kFinTX, kFinTY);
+    const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinRows - 1) / kFinRows, p.B), fblock(kFinTX, kFinTY);
     if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
