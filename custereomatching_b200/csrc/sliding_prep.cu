@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(128)
     const int wt = x / L.WTC, xin = x - wt * L.WTC;
     const int c0 = !col_ok ? 0 : img ? x - L.r + L.proj_lp : wt * L.seg_cam + xin;
     const int room_l = img ? 3 : min(3, xin), room_r = img ? 3 : min(3, L.seg_cam - (xin + K));
+    // in-image neighbours of the window inside the copy, to the left / right (0..3): constant per thread
+    const int nl = max(0, min(room_l, x - L.r)), nr = max(0, min(room_r, p.W - (x - L.r + K)));
     const float *src = (img ? projP : camP) + ((int64_t)b * L.NB + nb) * L.RBH * pitchP + c0;
     float *o1 = (img ? Sp : A) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
     float *o2 = (img ? ey2 : ex2) + ((int64_t)b * L.NB + nb) * L.RB * pitch + ci;
@@ -322,8 +324,8 @@ __global__ void __launch_bounds__(128)
             // (tiles that can see the zero padding do not slide): take the magnitude over that span
 #pragma unroll
             for (int j = 1; j <= 3; ++j) {
-                if (j <= room_l && x - L.r - j >= 0) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP - j]));
-                if (j <= room_r && x - L.r + K - 1 + j < p.W) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
+                if (j <= nl) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP - j]));
+                if (j <= nr) hm = fmaxf(hm, fabsf(src[(int64_t)t * pitchP + K - 1 + j]));
             }
         }
         float s1 = h1, s2 = h2, sm = hm;
