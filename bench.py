@@ -39,6 +39,8 @@ WORKLOADS = {
     "cfg2": (375, 1242, 192, 5, 1, "BASELINE configs[1]: one KITTI-size pair 1242x375, D=192, k=5"),
     "cfg3": (1988, 2880, 256, 5, 1, "BASELINE configs[2]: one Middlebury-full-size pair 2880x1988, D=256, k=5"),
     "cfg1": (240, 320, 64, 5, 1, "BASELINE configs[0]: one 320x240 pair, D=64, k=5"),
+    "cfg5band": (544, 7680, 512, 5, 1, "BASELINE configs[4] (one 7680x4320 pair, D=512, k=5, row-band over 8 GPUs): the "
+                                      "work of ONE rank - 540 volume rows plus the window-radius halo (sharding.row_band)"),
 }
 METRIC = "Mpix*disp/s fwd+bwd (cost-volume cells per second, forward+WTA+backward)"
 UNIT = "Mpix*disp/s"
