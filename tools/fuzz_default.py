@@ -56,6 +56,8 @@ for case in range(n):
     g1 = cb.backward(g, cam, proj, k, D)
     scale = float(g0.abs().max()) + 1e-30
     eg = float((g1 - g0).abs().max()) / scale
+    if eg > worst_g:
+        print(f'     new worst gradient error {eg:.2e} at {tag}', flush=True)
     if ec > worst_c:
         print(f'     new worst cost error {ec:.2e} at {tag}', flush=True)
     worst_c, worst_g = max(worst_c, ec), max(worst_g, eg)
