@@ -2,8 +2,8 @@
 // the main kernels stream into shared memory with no bounds checks and no per-element address arithmetic, and they
 // decide per tile whether the fast kernels may be used at all.
 //
-//   band_minmax_kernel        projector: min / max of the in-image pixels of every row band -> pivot = mid-range
-//   camera_tile_pivot_kernel  camera: the same per (band, column tile), over the tile's columns + window halo.
+//   pivot_kernel              projector: min / max of the in-image pixels of every row band -> pivot = mid-range;
+//                             camera: the same per (band, column tile), over the tile's columns + window halo.
 //                             ZNCC is invariant to a constant added to an image (reference kernel.cu:39-70 subtracts
 //                             the window mean); subtracting a local constant first keeps the raw products small,
 //                             which is what makes the O(1)-per-cell window sums safe in fp32.
@@ -157,37 +157,6 @@ int validate_sliding_layout(const Problem &p, bool backward) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    band_minmax_kernel(Problem p, SlidingLayout L, const float *__restrict__ proj, uint32_t *__restrict__ minmax) {
-    const int nb = blockIdx.y, img = 1, b = blockIdx.z;   // projector only: the camera has one pivot per column tile
-    const float *plane = proj + (int64_t)b * p.H * p.W;
-    const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RB + L.K - 1 - L.r);
-    const int64_t n = (int64_t)(y1 - y0) * p.W;
-    float vmax = -INFINITY, vmin = INFINITY;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = __ldg(plane + (int64_t)y0 * p.W + i);
-        vmax = fmaxf(vmax, v);
-        vmin = fminf(vmin, v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    }
-    __shared__ float smax[8], smin[8];
-    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = vmax; smin[threadIdx.x >> 5] = vmin; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int wi = 1; wi < 8; ++wi) { vmax = fmaxf(vmax, smax[wi]); vmin = fminf(vmin, smin[wi]); }
-        if (vmax >= vmin) {   // one pair of atomics per block
-            uint32_t *mm = minmax + ((size_t)(img * p.B + b) * L.NB + nb) * 2;
-            atomicMax(mm, float_to_ordered(vmax));
-            atomicMax(mm + 1, float_to_ordered(-vmin));
-        }
-    }
-}
-
 // camera pivot per (pair, band, column tile): mid-range of the in-image pixels of the tile's footprint (its columns plus
 // the window halo, the band's rows plus halo).  A block takes a run of whole tiles: one thread per image column marches
 // down the band's rows (coalesced, each pixel read once per band), the per-column extrema go to shared memory and one
@@ -195,14 +164,15 @@ __global__ void __launch_bounds__(256)
 // call: latency-bound and uncoalesced.)
 constexpr int kPivotThreads = 256;
 __global__ void __launch_bounds__(kPivotThreads)
-    camera_tile_pivot_kernel(Problem p, SlidingLayout L, int tiles_per_block, const float *__restrict__ cam,
-                             float *__restrict__ campiv) {
+    pivot_kernel(Problem p, SlidingLayout L, int tiles_per_block, const float *__restrict__ cam,
+                 const float *__restrict__ proj, float *__restrict__ campiv, uint32_t *__restrict__ minmax) {
     __shared__ float cmax[kPivotThreads], cmin[kPivotThreads];
-    const int nb = blockIdx.y, b = blockIdx.z, wt0 = blockIdx.x * tiles_per_block;
-    const float *plane = cam + (int64_t)b * p.H * p.W;
+    const bool is_proj = (int)blockIdx.z >= p.B;        // z >= B: the projector's band extrema (one pivot per band)
+    const int nb = blockIdx.y, b = blockIdx.z % p.B, wt0 = blockIdx.x * tiles_per_block;
+    const float *plane = (is_proj ? proj : cam) + (int64_t)b * p.H * p.W;
     const int y0 = max(0, nb * L.RB - L.r), y1 = min(p.H, nb * L.RB + L.RBH - L.r);
-    const int xb = wt0 * L.WTC - L.r;                                   // image column of thread 0
-    const int ncols = min(tiles_per_block, L.n_wtiles - wt0) * L.WTC + L.K - 1;
+    const int xb = wt0 * L.WTC - (is_proj ? 0 : L.r);                   // image column of thread 0
+    const int ncols = min(tiles_per_block, L.n_wtiles - wt0) * L.WTC + (is_proj ? 0 : L.K - 1);
     const int x = xb + (int)threadIdx.x;
     float vmax = -INFINITY, vmin = INFINITY;
     if ((int)threadIdx.x < ncols && x >= 0 && x < p.W) {
@@ -213,6 +183,25 @@ __global__ void __launch_bounds__(kPivotThreads)
             vmax = fmaxf(vmax, v);
             vmin = fminf(vmin, v);
         }
+    }
+    if (is_proj) {
+        // block-reduce, then one pair of atomics per block (non-negative keys: float_to_ordered is monotonic)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        }
+        if ((threadIdx.x & 31) == 0) { cmax[threadIdx.x >> 5] = vmax; cmin[threadIdx.x >> 5] = vmin; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int wi = 1; wi < kPivotThreads / 32; ++wi) { vmax = fmaxf(vmax, cmax[wi]); vmin = fminf(vmin, cmin[wi]); }
+            if (vmax >= vmin) {
+                uint32_t *mm = minmax + ((size_t)(p.B + b) * L.NB + nb) * 2;
+                atomicMax(mm, float_to_ordered(vmax));
+                atomicMax(mm + 1, float_to_ordered(-vmin));
+            }
+        }
+        return;
     }
     cmax[threadIdx.x] = vmax;
     cmin[threadIdx.x] = vmin;
@@ -403,14 +392,10 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
     float *rho_c = (float *)(ws + L.off_rho_c), *rho_p = (float *)(ws + L.off_rho_p);
     CUSTMA_CUDA_CHECK(cudaMemsetAsync(ws + L.off_minmax, 0, L.zero_end - L.off_minmax, stream));
     {
-        const int64_t n = (int64_t)L.RBH * p.W;
-        dim3 grid((unsigned)std::min<int64_t>((n + 4095) / 4096, 16), L.NB, p.B);
-        band_minmax_kernel<<<grid, 256, 0, stream>>>(p, L, proj, minmax);
-        CUSTMA_LAUNCH_CHECK("band_minmax_kernel");
         const int tiles_per_block = std::max(1, (kPivotThreads - (L.K - 1)) / L.WTC);
-        dim3 pgrid((L.n_wtiles + tiles_per_block - 1) / tiles_per_block, L.NB, p.B);
-        camera_tile_pivot_kernel<<<pgrid, kPivotThreads, 0, stream>>>(p, L, tiles_per_block, cam, campiv);
-        CUSTMA_LAUNCH_CHECK("camera_tile_pivot_kernel");
+        dim3 pgrid((L.n_wtiles + tiles_per_block - 1) / tiles_per_block, L.NB, 2 * p.B);
+        pivot_kernel<<<pgrid, kPivotThreads, 0, stream>>>(p, L, tiles_per_block, cam, proj, campiv, minmax);
+        CUSTMA_LAUNCH_CHECK("pivot_kernel");
     }
     {
         dim3 grid((std::max(L.cam_pitch, L.proj_pitch) / 4 + 255) / 256, L.NB * L.RBH, 2 * p.B);
