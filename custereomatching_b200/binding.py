@@ -22,7 +22,7 @@ ERR_UNSUPPORTED = 4
 FLAG_DIRECT = 1
 FLAG_TENSOR = 2
 INVALID_COST = -2.0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/custma_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = (
@@ -33,7 +33,10 @@ SYMBOLS = (
     "custma_forward_workspace_bytes",
     "custma_backward_workspace_bytes",
     "custma_forward",
+    "custma_forward_wta",
     "custma_backward",
+    "custma_backward_rows",
+    "custma_ingest_u8",
     "custma_host_step",
     "custma_host_submit",
     "custma_host_wait",
@@ -64,8 +67,16 @@ def _declare(lib):
     lib.custma_debug_validate_layout.argtypes = [_i32, _i32, _i32, _i32, _i32]
     lib.custma_forward.restype = ctypes.c_int
     lib.custma_forward.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_forward_wta.restype = ctypes.c_int
+    lib.custma_forward_wta.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_float, _i32, _i32, _i32, _i32,
+                                       _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward.restype = ctypes.c_int
     lib.custma_backward.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_backward_rows.restype = ctypes.c_int
+    lib.custma_backward_rows.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32, _ptr,
+                                         _size, _ptr]
+    lib.custma_ingest_u8.restype = ctypes.c_int
+    lib.custma_ingest_u8.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, ctypes.c_float, _ptr]
     lib.custma_host_step.restype = ctypes.c_int
     lib.custma_host_step.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32]
     lib.custma_host_submit.restype = ctypes.c_int
@@ -127,6 +138,26 @@ def forward(camera_ptr, projector_ptr, cost_ptr, best_ptr, index_ptr, B, H, W, D
     rc = load().custma_forward(camera_ptr, projector_ptr, cost_ptr or None, best_ptr or None, index_ptr or None,
                                B, H, W, D, k, flags, ws_ptr or None, ws_bytes, stream or None)
     check(rc, "custma_forward")
+
+
+def forward_wta(camera_ptr, projector_ptr, cost_ptr, best_ptr, index_ptr, mask_ptr, masked_disparity_ptr, threshold,
+                B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    rc = load().custma_forward_wta(camera_ptr, projector_ptr, cost_ptr or None, best_ptr or None, index_ptr or None,
+                                   mask_ptr or None, masked_disparity_ptr or None, float(threshold), B, H, W, D, k, flags,
+                                   ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_forward_wta")
+
+
+def backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin, row_end, flags, ws_ptr,
+                  ws_bytes, stream):
+    rc = load().custma_backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin,
+                                     row_end, flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_backward_rows")
+
+
+def ingest_u8(src_ptr, dst_ptr, B, H, W, channels, channel, scale, stream):
+    check(load().custma_ingest_u8(src_ptr, dst_ptr, B, H, W, channels, channel, float(scale), stream or None),
+          "custma_ingest_u8")
 
 
 def backward(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):

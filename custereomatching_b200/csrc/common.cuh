@@ -14,6 +14,9 @@ constexpr float kInvalid = CUSTMA_INVALID_COST;
 struct Problem {
     int32_t B, H, W, D, C, k, r;  // r = k / 2 (window offsets i - r, reference kernel.cu:44-46)
     int32_t banded;               // 0: last axis = projector column d ; 1: last axis = disparity s, d = w - s
+    int32_t g0, g1;               // backward only: volume rows [g0, g1) carry an upstream gradient and the gradient buffer
+                                  // is [B, g1 - g0, W, C]; the other rows count as zero (custma_backward_rows)
+    __host__ __device__ int32_t grows() const { return g1 - g0; }
     __host__ __device__ int64_t pixels() const { return (int64_t)B * H * W; }
     __host__ __device__ int64_t cells() const { return (int64_t)B * H * W * C; }
 };
@@ -22,6 +25,14 @@ struct Problem {
 __device__ __forceinline__ float query_ij(const float *__restrict__ img, int H, int W, int i, int j) {
     return (i < 0 || i >= H || j < 0 || j >= W) ? 0.f : __ldg(img + (int64_t)i * W + j);
 }
+
+// example-level outputs fused into the WTA decode (examples/verify.py:72-74, examples/test.py:78-86); all optional
+struct WtaExtras {
+    float *mask = nullptr;               // 1 where best > threshold else 0
+    float *masked_disparity = nullptr;   // (column - correspondence) * mask
+    float threshold = 0.6f;              // cost_volume_threshold, examples/verify.py:13
+};
+int launch_wta_extras(const Problem &p, const float *best, const int32_t *index, const WtaExtras &ex, cudaStream_t stream);
 
 // thread-local error message storage (custma_api.cu)
 int set_error(int code, const char *fmt, ...);
@@ -65,8 +76,8 @@ bool sliding_backward_supported(const Problem &p);
 size_t sliding_forward_workspace_bytes(const Problem &p);
 size_t sliding_backward_workspace_bytes(const Problem &p);
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
-                           int32_t *index, void *workspace, size_t workspace_bytes, bool force_tensor,
-                           cudaStream_t stream);
+                           int32_t *index, const WtaExtras &extras, void *workspace, size_t workspace_bytes,
+                           bool force_tensor, cudaStream_t stream);
 // tensor-core forward (tc_forward.cu): runs when fb_count is NULL or *fb_count > threshold, writes packed WTA keys
 bool tc_forward_supported(const Problem &p);
 int launch_tc_forward(const Problem &p, const float *cam, const float *proj, float *cost, unsigned long long *keys,

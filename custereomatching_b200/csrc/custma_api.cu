@@ -44,6 +44,7 @@ static int make_problem(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, P
     p->B = B; p->H = H; p->W = W; p->D = D; p->k = k; p->r = k / 2;
     p->banded = D > 0;
     p->C = D > 0 ? D : W;
+    p->g0 = 0; p->g1 = H;
     return CUSTMA_OK;
 }
 
@@ -61,6 +62,22 @@ static int carve_stats(const Problem &p, void *ws, size_t ws_bytes, size_t need,
     s->cmean = (float *)base; s->cex2 = (float *)(base + one);
     s->pmean = (float *)(base + 2 * one); s->pey2 = (float *)(base + 3 * one);
     s->rest = base + 4 * one; s->rest_bytes = ws_bytes - 4 * one;
+    return CUSTMA_OK;
+}
+
+// The vectorised banded kernels (D % 4 == 0) move the volume with 16-byte stores / cp.async: a misaligned pointer would
+// raise a sticky "misaligned address" fault instead of an error code, so it is rejected here.  Volumes whose last axis
+// is not a multiple of 4 floats are accessed element by element and need only 4-byte alignment.
+static int check_volume_alignment(const Problem &p, const void *ptr, const char *name) {
+    const uintptr_t need = (p.banded && (p.D & 3) == 0) ? 15u : 3u;
+    if (ptr && ((uintptr_t)ptr & need) != 0)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "%s must be %u-byte aligned for this shape (got %p)", name,
+                         (unsigned)need + 1u, ptr);
+    return CUSTMA_OK;
+}
+static int check_image_alignment(const void *ptr, const char *name) {
+    if (ptr && ((uintptr_t)ptr & 3u) != 0)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "%s must be 4-byte aligned (got %p)", name, ptr);
     return CUSTMA_OK;
 }
 
@@ -109,15 +126,22 @@ int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int
     return validate_sliding_layout(p, true);
 }
 
-int custma_forward(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
-                   int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
-                   size_t workspace_bytes, void *stream_) {
+static int forward_impl(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
+                        const WtaExtras &extras, int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags,
+                        void *workspace, size_t workspace_bytes, void *stream_) {
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);
     if (rc) return rc;
     if (!camera || !projector) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera and projector must not be NULL");
     if (!cost_volume && !best) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "no output requested (cost_volume and best are both NULL)");
     if ((best == nullptr) != (index == nullptr)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "best and index must be given together");
+    if ((extras.mask || extras.masked_disparity) && !best)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "mask / masked_disparity need best and index");
+    if ((rc = check_volume_alignment(p, cost_volume, "cost_volume"))) return rc;
+    if ((rc = check_image_alignment(camera, "camera")) || (rc = check_image_alignment(projector, "projector")) ||
+        (rc = check_image_alignment(best, "best")) || (rc = check_image_alignment(index, "index")) ||
+        (rc = check_image_alignment(extras.mask, "mask")) || (rc = check_image_alignment(extras.masked_disparity, "masked_disparity")))
+        return rc;
     if ((rc = check_device())) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
@@ -125,21 +149,46 @@ int custma_forward(const float *camera, const float *projector, float *cost_volu
     if ((flags & CUSTMA_FLAG_TENSOR) && ((flags & CUSTMA_FLAG_DIRECT) || !tc_forward_supported(p) || !sliding_forward_supported(p)))
         return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 572, k = 3 or 5, and no CUSTMA_FLAG_DIRECT");
     if (use_sliding_fwd(p, flags))
-        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, s.rest, s.rest_bytes,
+        return launch_sliding_forward(p, camera, projector, cost_volume, best, index, extras, s.rest, s.rest_bytes,
                                       (flags & CUSTMA_FLAG_TENSOR) != 0, stream);
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
-    return launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream);
+    if ((rc = launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream)))
+        return rc;
+    return best ? launch_wta_extras(p, best, index, extras, stream) : CUSTMA_OK;
 }
 
-int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
-                    int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
-                    size_t workspace_bytes, void *stream_) {
+int custma_forward(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
+                   int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
+                   size_t workspace_bytes, void *stream_) {
+    return forward_impl(camera, projector, cost_volume, best, index, WtaExtras(), B, H, W, D, k, flags, workspace,
+                        workspace_bytes, stream_);
+}
+
+int custma_forward_wta(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
+                       float *mask, float *masked_disparity, float mask_threshold, int32_t B, int32_t H, int32_t W,
+                       int32_t D, int32_t k, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    WtaExtras ex;
+    ex.mask = mask; ex.masked_disparity = masked_disparity; ex.threshold = mask_threshold;
+    return forward_impl(camera, projector, cost_volume, best, index, ex, B, H, W, D, k, flags, workspace, workspace_bytes,
+                        stream_);
+}
+
+static int backward_impl(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
+                         int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, int32_t row_begin, int32_t row_end,
+                         uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);
     if (rc) return rc;
     if (!cost_volume_grad || !camera || !projector || !camera_grad)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "cost_volume_grad, camera, projector and camera_grad must not be NULL");
+    if (row_begin < 0 || row_end > H || row_begin >= row_end)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "gradient rows [%d, %d) must be a non-empty range inside [0, %d)", row_begin, row_end, H);
+    p.g0 = row_begin; p.g1 = row_end;
+    if ((rc = check_volume_alignment(p, cost_volume_grad, "cost_volume_grad"))) return rc;
+    if ((rc = check_image_alignment(camera, "camera")) || (rc = check_image_alignment(projector, "projector")) ||
+        (rc = check_image_alignment(camera_grad, "camera_grad")))
+        return rc;
     if ((rc = check_device())) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     StatsPtrs s;
@@ -153,6 +202,43 @@ int custma_backward(const float *cost_volume_grad, const float *camera, const fl
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,
                                   (float *)s.rest, camera_grad, stream);
+}
+
+int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
+                    int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, void *workspace,
+                    size_t workspace_bytes, void *stream_) {
+    return backward_impl(cost_volume_grad, camera, projector, camera_grad, B, H, W, D, k, 0, H, flags, workspace,
+                         workspace_bytes, stream_);
+}
+
+int custma_backward_rows(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
+                         int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, int32_t row_begin, int32_t row_end,
+                         uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    return backward_impl(cost_volume_grad, camera, projector, camera_grad, B, H, W, D, k, row_begin, row_end, flags,
+                         workspace, workspace_bytes, stream_);
+}
+
+// uint8 ingestion (examples/verify.py:138-142,149: cv2.imread(...) / 255, channel 0 of the RGB image): one pass from the
+// interleaved 8-bit image to the fp32 plane the kernels read
+__global__ void __launch_bounds__(256)
+    ingest_u8_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst, int64_t pixels, int channels, int channel,
+                     float scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pixels) dst[i] = (float)src[i * channels + channel] * scale;
+}
+
+int custma_ingest_u8(const uint8_t *src, float *dst, int32_t B, int32_t H, int32_t W, int32_t channels, int32_t channel,
+                     float scale, void *stream_) {
+    if (!src || !dst) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "src and dst must not be NULL");
+    if (B <= 0 || H <= 0 || W <= 0 || channels < 1 || channel < 0 || channel >= channels)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "bad shape / channel: B=%d H=%d W=%d channels=%d channel=%d", B, H, W, channels, channel);
+    int rc = check_image_alignment(dst, "dst");
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    const int64_t pixels = (int64_t)B * H * W;
+    ingest_u8_kernel<<<(unsigned)((pixels + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, dst, pixels, channels, channel, scale);
+    CUSTMA_LAUNCH_CHECK("ingest_u8_kernel");
+    return CUSTMA_OK;
 }
 
 }  // extern "C"

@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
             const float ey2 = ey2_row[d];
             const float exy = cell_exy(camc, proj_plane, p.H, p.W, p.k, p.r, h, d, pm);
             const float den = sqrtf(fmaf(ex2, ey2, kEps));
-            const float g = grad[pix * p.C + c];
+            const int64_t bb = pix / ((int64_t)p.H * p.W);
+            const float g = (h >= p.g0 && h < p.g1) ? grad[((bb * p.grows() + (h - p.g0)) * p.W + w) * p.C + c] : 0.f;
             a = g / den;
             bsum += g * ey2 * (exy + kEps) / (den * den * den);
         }

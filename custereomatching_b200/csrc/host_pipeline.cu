@@ -72,15 +72,12 @@ static int32_t pick_chunk(int32_t B, int32_t H, int32_t W, int32_t D, bool strea
     return chunk;
 }
 
-static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume) {
-    int dev = 0;
-    CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
+// Builds every stream, event and buffer of the context.  g_ctx.live is set first so that release_locked() can take a
+// half-built context apart; ensure_ctx() does exactly that when anything here fails, so a later call never finds a
+// context that passes the cache test with null buffers in it.
+static int build_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume, int dev) {
     const int32_t C = D > 0 ? D : W;
     const size_t pair_vol = (size_t)H * W * C * sizeof(float);
-    if (g_ctx.live && g_ctx.device == dev && g_ctx.H == H && g_ctx.W == W && g_ctx.D == D && g_ctx.k == k &&
-        g_ctx.flags == flags && g_ctx.chunk >= chunk && (g_ctx.with_volume || !need_volume))
-        return CUSTMA_OK;
-    release_locked();
     g_ctx.live = true; g_ctx.device = dev; g_ctx.H = H; g_ctx.W = W; g_ctx.D = D; g_ctx.k = k; g_ctx.flags = flags;
     g_ctx.chunk = chunk; g_ctx.with_volume = need_volume;
     const size_t img = (size_t)chunk * H * W * sizeof(float);
@@ -103,6 +100,21 @@ static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k,
     for (auto &row : g_ctx.done)
         for (cudaEvent_t &e : row) CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return CUSTMA_OK;
+}
+
+static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume) {
+    int dev = 0;
+    CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_ctx.live && g_ctx.device == dev && g_ctx.H == H && g_ctx.W == W && g_ctx.D == D && g_ctx.k == k &&
+        g_ctx.flags == flags && g_ctx.chunk >= chunk && (g_ctx.with_volume || !need_volume))
+        return CUSTMA_OK;
+    release_locked();
+    const int rc = build_ctx(chunk, H, W, D, k, flags, need_volume, dev);
+    if (rc != CUSTMA_OK) {
+        release_locked();          // e.g. out of memory on the volume buffer: leave no half-built context behind
+        cudaGetLastError();        // and no sticky allocation error for the caller's next CUDA call
+    }
+    return rc;
 }
 
 }  // namespace custma

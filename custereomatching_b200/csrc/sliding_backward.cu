@@ -40,8 +40,11 @@ struct BwdGeom {
     static constexpr int TW = F::WTC + K - 1;                    // columns of a T1 tile row
     static_assert(TW <= 96 && 96 + 2 * F::WTC <= F::NCONS, "reduce_step thread ranges");
     static constexpr int XPOSE_STRIDE = 20;                     // floats per lane row of the transpose scratch
+    // per-unit scratch: 16 lane rows + 16 floats of padding - without it the two units of a warp (320 floats apart, a
+    // multiple of 32 banks) collide on every scalar read of the transpose (ncu: 44 % of those wavefronts were excessive)
+    static constexpr int XPOSE_UNIT = 16 * XPOSE_STRIDE + 16;
     // row ring | gradient ring (+ one stage that stays zero) | transpose scratch (16 lanes x 20 floats per unit)
-    static constexpr int GRAD_FLOATS = (kGradStages + 1) * 16 * F::NCONS, XPOSE_FLOATS = UNITS * 16 * XPOSE_STRIDE;
+    static constexpr int GRAD_FLOATS = (kGradStages + 1) * 16 * F::NCONS, XPOSE_FLOATS = UNITS * XPOSE_UNIT;
     static constexpr int SMEM_FLOATS = F::NS * SLOT + GRAD_FLOATS + XPOSE_FLOATS;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_FLOATS * sizeof(float);
 };
@@ -172,7 +175,9 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     const float seed = kEps / (float)K, inv_n = 1.f / (float)(K * K);
     float *gsm = smem + NS * G::SLOT;   // [kGradStages][4][NT] float4
     // upstream gradient of (row h0, column w0, disparity s0); row hr, column i: + (hr*W + i) * C
-    const float *gsrc = grad + (((int64_t)b * p.H + h0) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
+    // (the gradient buffer holds volume rows [p.g0, p.g1) only: custma_backward_rows)
+    const float *gsrc = grad + (((int64_t)b * p.grows() + (h0 - p.g0)) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
+    const int g_lo = max(0, p.g0 - h0), g_hi = min(rows, p.g1 - h0);   // band rows that carry a gradient
     uint32_t cmask = 0;  // MODE 1: bit 4i+j = cell (w0+i, s0+j) exists and is valid; constant over the band's rows
     if (MODE == 1) {
 #pragma unroll
@@ -183,7 +188,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     }
     const int64_t g_row = (int64_t)p.W * C;
 
-    float *xps = gsm + G::GRAD_FLOATS + u * (16 * G::XPOSE_STRIDE);   // this unit's transpose scratch
+    float *xps = gsm + G::GRAD_FLOATS + u * G::XPOSE_UNIT;   // this unit's transpose scratch
     const float *gzero = gsm + (kGradStages * 4) * (4 * NT) + 4 * tid;  // a stage that is never written: stays zero
 
     BoxRing<K> ring;
@@ -241,7 +246,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             // ---- prefetch the upstream gradient row that step t + GLA consumes
             if (MODE != 2) {
                 const int hp = t + GLA - (K - 1);
-                if (hp >= 0 && hp < rows) {
+                if (hp >= g_lo && hp < g_hi) {
                     float *gdst = gsm + ((hp & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -253,7 +258,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             mbar_wait(&full_bar[slot], (t / NS) & 1);
             float *S = smem + slot * G::SLOT;
             const int hr = t - (K - 1);
-            const bool has_cells = hr >= 0 && hr < rows;
+            const bool has_cells = hr >= g_lo && hr < g_hi;
 
             float c[CL], pj[PL];
 #pragma unroll
@@ -371,6 +376,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
         reduce_step(ts);
     }
 }
+
 
 template <int K, int NU, int WG>
 __global__ void __launch_bounds__(16 * NU * WG, 1)

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                 const float ey2 = fb_ey2[o];
                 const float exy = cell_exy(p, proj_plane, camc, h, d, pm);
                 const float den = sqrtf(fmaf(ex2, ey2, kEps));
-                const float g = grad[pix * p.C + c];
+                const float g = (h >= p.g0 && h < p.g1) ? grad[(((int64_t)b * p.grows() + (h - p.g0)) * p.W + w) * p.C + c] : 0.f;
                 a = g / den;                                          // reference :135,:145
                 bsum += g * ey2 * (exy + kEps) / (den * den * den);   // reference :147
             }

@@ -209,16 +209,40 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
     }
 }
 
-// best / index from the packed keys
+// best / index from the packed keys, and the example-level outputs that depend on nothing else: the confidence mask
+// best > threshold (examples/verify.py:74) and the masked disparity (column - correspondence) * mask
+// (examples/test.py:83-84) - s already is column - correspondence
 __global__ void __launch_bounds__(256)
     wta_decode_kernel(Problem p, const unsigned long long *__restrict__ keys, float *__restrict__ best,
-                      int32_t *__restrict__ index) {
+                      int32_t *__restrict__ index, const WtaExtras ex) {
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p.pixels()) return;
     const unsigned long long key = keys[pix];
     const int s = (int)(uint32_t)(key & 0xffffffffu) - p.W;
-    best[pix] = ordered_to_float((uint32_t)(key >> 32));
+    const float bv = ordered_to_float((uint32_t)(key >> 32));
+    best[pix] = bv;
     index[pix] = p.banded ? s : (int)(pix % p.W) - s;
+    const float m = bv > ex.threshold ? 1.f : 0.f;
+    if (ex.mask) ex.mask[pix] = m;
+    if (ex.masked_disparity) ex.masked_disparity[pix] = (float)s * m;
+}
+
+// the same two outputs for the paths that write best / index themselves (direct kernels)
+__global__ void __launch_bounds__(256)
+    wta_extras_kernel(Problem p, const float *__restrict__ best, const int32_t *__restrict__ index, const WtaExtras ex) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.pixels()) return;
+    const float m = best[pix] > ex.threshold ? 1.f : 0.f;
+    const int idx = index[pix];
+    if (ex.mask) ex.mask[pix] = m;
+    if (ex.masked_disparity) ex.masked_disparity[pix] = (float)(p.banded ? idx : (int)(pix % p.W) - idx) * m;
+}
+
+int launch_wta_extras(const Problem &p, const float *best, const int32_t *index, const WtaExtras &ex, cudaStream_t stream) {
+    if (!ex.mask && !ex.masked_disparity) return CUSTMA_OK;
+    wta_extras_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, best, index, ex);
+    CUSTMA_LAUNCH_CHECK("wta_extras_kernel");
+    return CUSTMA_OK;
 }
 
 template <int K, int NU, int WG, bool COST, bool WTA>
@@ -272,8 +296,8 @@ size_t sliding_forward_workspace_bytes(const Problem &p) {
 constexpr double kTensorShare = 0.04;
 
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
-                           int32_t *index, void *workspace, size_t workspace_bytes, bool force_tensor,
-                           cudaStream_t stream) {
+                           int32_t *index, const WtaExtras &extras, void *workspace, size_t workspace_bytes,
+                           bool force_tensor, cudaStream_t stream) {
     SlidingConfig cfg;
     if (!sliding_pick_config(p, false, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
@@ -301,7 +325,7 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
             return rc;
     }
     if (best) {
-        wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index);
+        wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index, extras);
         CUSTMA_LAUNCH_CHECK("wta_decode_kernel");
     }
     return CUSTMA_OK;

@@ -295,14 +295,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     if (tid < 18 * NQ) {
                         const int g4 = tid % NQ, row0 = tid / NQ;
                         const int s_off = blk * PW - (MT + 3) + 4 * g4;
-                        const float *gbase = grad + ((int64_t)b * H + y) * W * D;
+                        const bool grow = y >= p.g0 && y < p.g1;        // rows outside [g0, g1) carry no gradient
+                        const float *gbase = grad + ((int64_t)b * p.grows() + (grow ? y - p.g0 : 0)) * W * D;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const int Lr = row0 + 18 * k;
                             const int qL = Lr >> 5, mL = 4 * (Lr & 31) + qL, xr = x0 + mL;
                             const int s = mL + s_off + ((3 - qL) & 3);
                             if (Lr < MT) {
-                                const bool live = xr < W && (unsigned)s < (unsigned)D;
+                                const bool live = grow && xr < W && (unsigned)s < (unsigned)D;
                                 const float *src = live ? gbase + (int64_t)xr * D + s : gbase;
                                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&S.stage[Lr][4 * g4])), "l"(src),
                                              "r"(live ? 16 : 0) : "memory");

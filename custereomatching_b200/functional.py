@@ -53,6 +53,12 @@ def _shape_bhw(camera: torch.Tensor, projector: torch.Tensor) -> Tuple[int, int,
     return B, H, W, batched
 
 
+def _aligned16(x: torch.Tensor) -> torch.Tensor:
+    """The banded kernels move the volume with 128-bit accesses (include/custma_b200.h, "Alignment"): a contiguous view
+    whose storage offset is not a multiple of 16 bytes is copied to a fresh (512-byte aligned) allocation."""
+    return x if x.data_ptr() % 16 == 0 else x.clone(memory_format=torch.contiguous_format)
+
+
 def _workspace(nbytes: int, device) -> Tuple[Optional[torch.Tensor], int]:
     if nbytes == 0:
         return None, 0
@@ -61,19 +67,24 @@ def _workspace(nbytes: int, device) -> Tuple[Optional[torch.Tensor], int]:
 
 
 def forward(camera: torch.Tensor, projector: torch.Tensor, D: int = 0, kernel_size: int = 5, *,
-            want_cost: bool = True, want_wta: bool = False, flags: int = 0):
+            want_cost: bool = True, want_wta: bool = False, flags: int = 0, want_mask: bool = False,
+            mask_threshold: float = 0.6):
     """ZNCC cost volume and / or winner-take-all.
 
     camera, projector: float32 CUDA, [H,W] or [B,H,W].  D == 0: reference-shaped volume [...,H,W,W] whose last axis
     is the projector column; D > 0: banded volume [...,H,W,D] whose last axis is the disparity s (projector column
     w - s; cells with w - s < 0 hold INVALID_COST).  Returns (cost | None, best | None, index | None); index is
     int32: first maximal projector column (D == 0) or the disparity of it (D > 0).
+    want_mask (needs want_wta): two more results from the same decode kernel - the confidence mask best > mask_threshold
+    (examples/verify.py:74) and the masked disparity (column - correspondence) * mask (examples/test.py:83-84), both fp32.
     """
     _check_input(camera, "camera")
     _check_input(projector, "projector")
     B, H, W, batched = _shape_bhw(camera, projector)
     if not (want_cost or want_wta):
         raise RuntimeError("nothing to compute: want_cost and want_wta are both False")
+    if want_mask and not want_wta:
+        raise RuntimeError("want_mask needs want_wta")
     D = int(D)
     k = int(kernel_size)
     C = D if D > 0 else W
@@ -82,24 +93,36 @@ def forward(camera: torch.Tensor, projector: torch.Tensor, D: int = 0, kernel_si
         cost = torch.empty(lead + (H, W, C), dtype=torch.float32, device=camera.device) if want_cost else None
         best = torch.empty(lead + (H, W), dtype=torch.float32, device=camera.device) if want_wta else None
         index = torch.empty(lead + (H, W), dtype=torch.int32, device=camera.device) if want_wta else None
+        mask = torch.empty(lead + (H, W), dtype=torch.float32, device=camera.device) if want_mask else None
+        mdisp = torch.empty(lead + (H, W), dtype=torch.float32, device=camera.device) if want_mask else None
         nbytes = binding.forward_workspace_bytes(B, H, W, D, k, flags)
         if nbytes == 0:  # the query validates the arguments; every valid problem needs a non-empty workspace
             binding.check(binding.ERR_INVALID_ARGUMENT, "custma_forward_workspace_bytes")
         ws, ws_ptr = _workspace(nbytes, camera.device)
         stream = torch.cuda.current_stream(camera.device).cuda_stream
-        binding.forward(camera.data_ptr(), projector.data_ptr(),
-                        cost.data_ptr() if cost is not None else 0,
-                        best.data_ptr() if best is not None else 0,
-                        index.data_ptr() if index is not None else 0,
-                        B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        if want_mask:
+            binding.forward_wta(camera.data_ptr(), projector.data_ptr(), cost.data_ptr() if cost is not None else 0,
+                                best.data_ptr(), index.data_ptr(), mask.data_ptr(), mdisp.data_ptr(), mask_threshold,
+                                B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        else:
+            binding.forward(camera.data_ptr(), projector.data_ptr(),
+                            cost.data_ptr() if cost is not None else 0,
+                            best.data_ptr() if best is not None else 0,
+                            index.data_ptr() if index is not None else 0,
+                            B, H, W, D, k, flags, ws_ptr, nbytes, stream)
         if ws is not None:
             ws.record_stream(torch.cuda.current_stream(camera.device))
+    if want_mask:
+        return cost, best, index, mask, mdisp
     return cost, best, index
 
 
 def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: torch.Tensor, kernel_size: int,
-             D: int = 0, *, flags: int = 0) -> torch.Tensor:
-    """Gradient of sum(cost * cost_volume_grad) with respect to the camera image; same leading shape as camera."""
+             D: int = 0, *, flags: int = 0, rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Gradient of sum(cost * cost_volume_grad) with respect to the camera image; same leading shape as camera.
+
+    rows = (row_begin, row_end): the upstream gradient exists only on those volume rows and cost_volume_grad is
+    [..., row_end - row_begin, W, C] (custma_backward_rows: what a row-band shard passes for its owned rows)."""
     _check_input(cost_volume_grad, "cost_volume_grad")
     _check_input(camera, "camera")
     _check_input(projector, "projector")
@@ -107,11 +130,15 @@ def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: to
     D = int(D)
     C = D if D > 0 else W
     lead = (B,) if batched else ()
-    if tuple(cost_volume_grad.shape) != lead + (H, W, C):
-        raise RuntimeError(f"cost_volume_grad must have shape {lead + (H, W, C)}, got {tuple(cost_volume_grad.shape)}")
+    r0, r1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 < r1 <= H:
+        raise RuntimeError(f"rows {rows} must be a non-empty range inside [0, {H})")
+    if tuple(cost_volume_grad.shape) != lead + (r1 - r0, W, C):
+        raise RuntimeError(f"cost_volume_grad must have shape {lead + (r1 - r0, W, C)}, got {tuple(cost_volume_grad.shape)}")
     if cost_volume_grad.device != camera.device:
         raise RuntimeError("cost_volume_grad must be on the images' device")
     k = int(kernel_size)
+    cost_volume_grad = _aligned16(cost_volume_grad)
     with torch.cuda.device(camera.device):
         camera_grad = torch.empty_like(camera)
         nbytes = binding.backward_workspace_bytes(B, H, W, D, k, flags)
@@ -119,8 +146,12 @@ def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: to
             binding.check(binding.ERR_INVALID_ARGUMENT, "custma_backward_workspace_bytes")
         ws, ws_ptr = _workspace(nbytes, camera.device)
         stream = torch.cuda.current_stream(camera.device).cuda_stream
-        binding.backward(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
-                         camera_grad.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        if rows is None:
+            binding.backward(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
+                             camera_grad.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+        else:
+            binding.backward_rows(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
+                                  camera_grad.data_ptr(), B, H, W, D, k, r0, r1, flags, ws_ptr, nbytes, stream)
         if ws is not None:
             ws.record_stream(torch.cuda.current_stream(camera.device))
     return camera_grad
@@ -162,6 +193,44 @@ def cost_volume_and_wta(camera, projector, D: int = 0, kernel_size: int = 5, fla
     return forward(camera, projector, D, kernel_size, want_cost=True, want_wta=True, flags=flags)
 
 
+def wta_masked(camera, projector, D: int = 0, kernel_size: int = 5, threshold: float = 0.6, flags: int = 0):
+    """Fused forward + winner-take-all + confidence mask, no volume: (best, index, mask, masked_disparity).
+
+    mask = best > threshold (examples/verify.py:72-74, cost_volume_threshold = 0.6 at :13) and
+    masked_disparity = (column - correspondence) * mask (examples/test.py:83-84) come out of the kernel that decodes the
+    WTA keys - no torch op touches the results."""
+    _, best, index, mask, mdisp = forward(camera, projector, D, kernel_size, want_cost=False, want_wta=True, flags=flags,
+                                          want_mask=True, mask_threshold=threshold)
+    return best, index, mask, mdisp
+
+
+def ingest_u8(image_u8: torch.Tensor, channel: int = 0, scale: float = 1.0 / 255.0) -> torch.Tensor:
+    """uint8 CUDA image [H,W], [H,W,Ch], [B,H,W,Ch] -> float32 plane(s) of one channel times scale
+    (examples/verify.py:138-142,149: cv2.imread(...) / 255, then [:, :, 0])."""
+    if not isinstance(image_u8, torch.Tensor) or not image_u8.is_cuda:
+        raise RuntimeError("image must be a CUDA tensor")
+    if image_u8.dtype != torch.uint8:
+        raise RuntimeError(f"image must be a uint8 tensor, got {image_u8.dtype}")
+    if not image_u8.is_contiguous():
+        raise RuntimeError("image must be contiguous")
+    if image_u8.dim() == 2:
+        lead, (H, W), ch = (), image_u8.shape, 1
+    elif image_u8.dim() == 3:
+        lead, (H, W, ch) = (), image_u8.shape
+    elif image_u8.dim() == 4:
+        lead, (H, W, ch) = (image_u8.shape[0],), image_u8.shape[1:]
+    else:
+        raise RuntimeError(f"image must be [H,W], [H,W,Ch] or [B,H,W,Ch], got {tuple(image_u8.shape)}")
+    B = lead[0] if lead else 1
+    if B == 0 or H == 0 or W == 0:
+        raise RuntimeError(f"empty input {tuple(image_u8.shape)}")
+    with torch.cuda.device(image_u8.device):
+        out = torch.empty(lead + (H, W), dtype=torch.float32, device=image_u8.device)
+        binding.ingest_u8(image_u8.data_ptr(), out.data_ptr(), B, H, W, ch, int(channel), scale,
+                          torch.cuda.current_stream(image_u8.device).cuda_stream)
+    return out
+
+
 def confidence_mask(best: torch.Tensor, threshold: float = 0.6) -> torch.Tensor:
-    """examples/verify.py:74: 1 where the best ZNCC exceeds the threshold, else 0 (same dtype as best)."""
+    """examples/verify.py:74 as a torch expression (for results that already exist); the fused form is wta_masked()."""
     return (best > threshold).to(best.dtype)

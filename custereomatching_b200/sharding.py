@@ -57,6 +57,10 @@ class RowBand:
 
 
 def row_band(H: int, kernel_size: int, rank: int, world: int) -> RowBand:
+    if world > H:
+        # checked identically on every rank BEFORE any collective: an empty band would fail on its own rank while the
+        # others wait in all_gather
+        raise ValueError(f"row-band sharding needs at least one volume row per rank: H={H} < world={world}")
     h0, h1 = split_even(H, world)[rank]
     r = kernel_size // 2
     if h1 == h0:
@@ -158,10 +162,12 @@ def assemble_row_band_gradient(grad_on_crop: torch.Tensor, H: int, kernel_size: 
 
 # ---- GPU-side drivers (need the CUDA library; exercised by the -m gpu tests and bench.py) ------------------------
 def batch_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int, kernel_size: int,
-                       cost_volume_grad_fn=None, gather: bool = True, group=None):
+                       cost_volume_grad_fn=None, gather: bool = True, group=None, global_batch: Optional[int] = None):
     """One forward(+WTA)(+backward) over THIS rank's batch slice [b_r,H,W] already resident on its GPU.
 
     cost_volume_grad_fn(cost) -> upstream gradient (the caller's loss); None skips the backward.
+    global_batch: the size of the whole batch (the slices are batch_slice(global_batch, rank, world)); when None it is
+    found with one small all_gather + host read per call - pass it in a training loop.
     Returns (best, disparity, camera_grad | None), gathered over ranks to the full batch when gather=True."""
     from . import functional as F
     rank, world = _world(group)
@@ -171,7 +177,7 @@ def batch_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int, ke
     if cost_volume_grad_fn is not None:
         grad = F.backward(cost_volume_grad_fn(cost), camera, projector, kernel_size, D)
     if gather and world > 1:
-        B = sum(_gather_sizes(camera.shape[0], group))
+        B = int(global_batch) if global_batch is not None else sum(_gather_sizes(camera.shape[0], group))
         best = all_gather_batch(best, B, group)
         disp = all_gather_batch(disp, B, group)
         if grad is not None:
@@ -206,11 +212,10 @@ def row_band_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int,
                                  want_wta=True)
     grad = None
     if cost_volume_grad_fn is not None:
-        g = cost_volume_grad_fn(band_rows_of(cost, band), band)       # gradient of the OWNED rows only
-        g_crop = torch.zeros_like(cost)
-        b0, b1 = band_gradient_mask_rows(band)
-        g_crop[b0:b1] = g
-        grad = F.backward(g_crop, cam_c, proj_c, kernel_size, D)
+        # gradient of the OWNED rows only, handed over as it is: custma_backward_rows treats the halo rows of the crop as
+        # zero, so no volume-sized zero fill or copy happens here
+        g = cost_volume_grad_fn(band_rows_of(cost, band), band)
+        grad = F.backward(g.contiguous(), cam_c, proj_c, kernel_size, D, rows=band_gradient_mask_rows(band))
         grad = assemble_row_band_gradient(grad, H, kernel_size, group)
     best = all_gather_row_bands(band_rows_of(best, band), H, kernel_size, group)
     disp = all_gather_row_bands(band_rows_of(disp, band), H, kernel_size, group)

@@ -29,6 +29,11 @@
  *   camera_grad         [B, H, W]
  * The reference has no batch axis (B == 1) and ignores D (custma/src/stereo_matching_kernel.cu:14): its behaviour is
  * B = 1, D = 0 here.
+ *
+ * Alignment: the workspace must be 256-byte aligned; images and [B,H,W] results 4-byte aligned; cost_volume and
+ * cost_volume_grad 16-byte aligned when the volume is banded with D % 4 == 0 (the kernels move it with 128-bit
+ * accesses), 4-byte aligned otherwise.  A pointer that violates this is refused with CUSTMA_ERR_INVALID_ARGUMENT
+ * (a view at an odd storage offset must be copied by the caller; custereomatching_b200.functional does).
  */
 #ifndef CUSTMA_B200_H_
 #define CUSTMA_B200_H_
@@ -40,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CUSTMA_ABI_VERSION 1
+#define CUSTMA_ABI_VERSION 2
 
 #define CUSTMA_OK 0
 #define CUSTMA_ERR_INVALID_ARGUMENT 1 /* null pointer, non-positive size, kernel_size out of range, ... */
@@ -81,11 +86,35 @@ int custma_forward(const float *camera, const float *projector, float *cost_volu
                    int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* custma_forward plus the example-level outputs that depend only on the winner (examples/verify.py:72-74,
+ * examples/test.py:78-86), written by the same kernel that decodes the WTA:
+ *   mask              [B,H,W] fp32: 1 where best > mask_threshold, else 0 (cost_volume_threshold = 0.6 in verify.py:13)
+ *   masked_disparity  [B,H,W] fp32: (column - correspondence) * mask, i.e. the winning disparity, zeroed where the
+ *                     match is not confident
+ * Either may be NULL; both need best and index. */
+int custma_forward_wta(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
+                       float *mask, float *masked_disparity, float mask_threshold, int32_t B, int32_t H, int32_t W,
+                       int32_t D, int32_t kernel_size, uint32_t flags, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 /* Backward: gradient of sum(cost_volume * cost_volume_grad) with respect to the camera image only
  * (custma/stereo_matching_wrapper.py:33).  Deterministic: no global atomics anywhere.  camera_grad is overwritten. */
 int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
                     int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* Backward for an upstream gradient that exists only on volume rows [row_begin, row_end): cost_volume_grad is
+ * [B, row_end - row_begin, W, C]; all other rows count as zero.  camera_grad is still [B,H,W] (rows the window cannot
+ * reach come out as 0).  This is what a row-band shard calls (one rank owns rows [row_begin, row_end) of the volume
+ * computed on its haloed crop): no volume-sized zero fill or copy on the caller's side. */
+int custma_backward_rows(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
+                         int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, int32_t row_begin,
+                         int32_t row_end, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/* 8-bit ingestion (examples/verify.py:138-142,149 load PNGs with cv2, divide by 255 and take channel 0):
+ * dst[b,h,w] = src[b,h,w,channel] * scale for an interleaved uint8 image [B,H,W,channels] in device memory. */
+int custma_ingest_u8(const uint8_t *src, float *dst, int32_t B, int32_t H, int32_t W, int32_t channels, int32_t channel,
+                     float scale, void *stream);
 
 /* Host-buffer step (what a non-torch caller binds): images in host memory (pinned for full copy speed), results
  * back in host memory.  Runs forward + WTA and, when cost_volume_grad_dev is non-NULL, backward, pair by pair on
@@ -99,7 +128,11 @@ int custma_host_step(const float *h_camera, const float *h_projector, float *h_b
 /* The same step without the final wait, for callers that stream batches: returns once everything is enqueued and
  * stores a ticket; the host buffers of a ticket may be read (results) or rewritten (images) after
  * custma_host_wait(ticket) - 0 waits for everything submitted so far.  Consecutive submits overlap: the copies of
- * one step run under the kernels of the other, so keep two sets of host result buffers. */
+ * one step run under the kernels of the other, so keep two sets of host result buffers.
+ * Device buffers: the library reads cost_volume_grad_dev and writes cost_volume_dev on its own non-blocking streams,
+ * which are NOT ordered after the stream the caller produced the gradient on: the gradient must be complete (event or
+ * stream synchronised) before the submit, and two tickets that may be in flight together must not share a
+ * cost_volume_dev (pass two volumes alternately, or NULL to use the library's per-slot volumes). */
 int custma_host_submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
                        float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                        int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, uint64_t *ticket);
