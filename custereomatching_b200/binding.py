@@ -12,7 +12,8 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libcustma_b200.so")
+# CUSTMA_LIB: another build of the same library (kernel experiments, tools/build_variants.py); never a different backend
+LIB_PATH = os.environ.get("CUSTMA_LIB") or os.path.join(PKG_DIR, "libcustma_b200.so")
 
 OK = 0
 ERR_INVALID_ARGUMENT = 1
