@@ -31,6 +31,7 @@ SYMBOLS = (
     "custma_last_error",
     "custma_launch_count",
     "custma_debug_validate_layout",
+    "custma_debug_verdict_info",
     "custma_forward_workspace_bytes",
     "custma_backward_workspace_bytes",
     "custma_forward",
@@ -66,6 +67,9 @@ def _declare(lib):
         fn.argtypes = [_i32, _i32, _i32, _i32, _i32, _u32]
     lib.custma_debug_validate_layout.restype = ctypes.c_int
     lib.custma_debug_validate_layout.argtypes = [_i32, _i32, _i32, _i32, _i32]
+    lib.custma_debug_verdict_info.restype = ctypes.c_int
+    lib.custma_debug_verdict_info.argtypes = [_i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_size),
+                                              ctypes.POINTER(_u32), ctypes.POINTER(_i32)]
     lib.custma_forward.restype = ctypes.c_int
     lib.custma_forward.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_forward_wta.restype = ctypes.c_int
@@ -125,6 +129,15 @@ def check(rc: int, what: str) -> None:
 
 def validate_layout(B, H, W, D, k) -> None:
     check(load().custma_debug_validate_layout(B, H, W, D, k), "custma_debug_validate_layout")
+
+
+def debug_layout_info(B, H, W, D, k):
+    """Where custma_forward leaves its conditioning verdict in the workspace (None if the shape has no fast path)."""
+    off, cap, tc = _size(0), _u32(0), _i32(0)
+    rc = load().custma_debug_verdict_info(B, H, W, D, k, ctypes.byref(off), ctypes.byref(cap), ctypes.byref(tc))
+    if rc != OK:
+        return None
+    return {"fb_count_offset": int(off.value), "fb_capacity": int(cap.value), "tc_supported": bool(tc.value)}
 
 
 def forward_workspace_bytes(B, H, W, D, k, flags=0) -> int:

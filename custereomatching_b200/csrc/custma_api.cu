@@ -118,6 +118,22 @@ size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t 
     return backward_ws(p, flags);
 }
 
+int custma_debug_verdict_info(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, size_t *count_offset,
+                              uint32_t *capacity, int32_t *tensor_core_available) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, false, &cfg))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel (hence no verdict) for k=%d", k);
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, false, &L);
+    if (count_offset) *count_offset = stats_bytes(p) + L.off_fb_count;
+    if (capacity) *capacity = (uint32_t)((int64_t)p.B * L.NB * L.n_wtiles * L.fb_groups);
+    if (tensor_core_available) *tensor_core_available = tc_forward_supported(p) ? 1 : 0;
+    return CUSTMA_OK;
+}
+
 int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k) {
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);

@@ -25,7 +25,6 @@ namespace custma {
 
 constexpr int kGradStages = 4;     // ring of upstream-gradient rows in shared memory
 constexpr int kGradLookahead = 3;  // steps between issuing a gradient row and using it
-constexpr int kGradL2Ahead = 8;    // CUSTMA_BWD_LDG: steps between the L2 prefetch of a gradient row and its loads
 constexpr int kBwdLookahead = 4;   // row slots are refilled 4 steps ahead, from the slot every warp released 4 steps ago
                                    // (8 slots): warps may drift up to 4 steps apart before anyone waits
 
@@ -45,7 +44,7 @@ struct BwdGeom {
     // multiple of 32 banks) collide on every scalar read of the transpose (ncu: 44 % of those wavefronts were excessive)
     static constexpr int XPOSE_UNIT = 16 * XPOSE_STRIDE + 16;
     // row ring | gradient ring (+ one stage that stays zero) | transpose scratch (16 lanes x 20 floats per unit)
-    static constexpr int GRAD_FLOATS = (kGradStages + 1) * 16 * F::NCONS, XPOSE_PAR = UNITS * XPOSE_UNIT, XPOSE_FLOATS = 2 * XPOSE_PAR;
+    static constexpr int GRAD_FLOATS = (kGradStages + 1) * 16 * F::NCONS, XPOSE_FLOATS = UNITS * XPOSE_UNIT;
     static constexpr int SMEM_FLOATS = F::NS * SLOT + GRAD_FLOATS + XPOSE_FLOATS;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_FLOATS * sizeof(float);
 };
@@ -196,9 +195,6 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     SumRing<K> vring;
     ring.clear();
     vring.clear();
-#ifdef CUSTMA_BWD_EARLY
-    uint32_t ready = 0;   // bit 0 / 1: the full / empty barrier test issued one step early succeeded
-#endif
 
     // fixed-order sum of the per-unit partials of step ts (every warp has arrived on its empty barrier) -> workspace
     auto reduce_step = [&](int ts) {
@@ -243,25 +239,11 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             // ---- refill the slot of step t + lookahead (used last by step t + lookahead - 8), after finishing that step's sums
             if (t >= NS - kBwdLookahead) {
                 const int ts = t - (NS - kBwdLookahead);
-#ifdef CUSTMA_BWD_EARLY
-                if (!(ready & 2u))
-#endif
                 mbar_wait(&empty_bar[ts & (NS - 1)], (ts / NS) & 1);
                 reduce_step(ts);
             }
             if (t + kBwdLookahead < steps) loader.issue(t + kBwdLookahead, smem, full_bar);
             // ---- prefetch the upstream gradient row that step t + GLA consumes
-#ifdef CUSTMA_BWD_LDG
-            if (MODE != 2) {   // into L2 only; the row is read with plain 128-bit loads when its step comes
-                const int hp = t + kGradL2Ahead - (K - 1);
-                if (hp >= g_lo && hp < g_hi && (l16 & 7) == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (MODE == 0 || w0 + i < p.W)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc + hp * g_row + (int64_t)i * C));
-                }
-            }
-#else
             if (MODE != 2) {
                 const int hp = t + GLA - (K - 1);
                 if (hp >= g_lo && hp < g_hi) {
@@ -273,40 +255,12 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
-#endif
-#ifdef CUSTMA_BWD_EARLY
-            if (!(ready & 1u))
-#endif
             mbar_wait(&full_bar[slot], (t / NS) & 1);
             float *S = smem + slot * G::SLOT;
             const int hr = t - (K - 1);
             const bool has_cells = hr >= g_lo && hr < g_hi;
 
             float gg[4][4];
-#ifdef CUSTMA_BWD_LDG
-            if (MODE != 2) {   // issued before the window ring runs: an L2 hit (prefetched above) lands under its arithmetic
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_cells && (MODE == 0 || w0 + i < p.W))
-                        v = __ldcs(reinterpret_cast<const float4 *>(gsrc + hr * g_row + (int64_t)i * C));
-                    gg[i][0] = v.x; gg[i][1] = v.y; gg[i][2] = v.z; gg[i][3] = v.w;
-                }
-            }
-#endif
-#ifdef CUSTMA_BWD_DEFER
-            float prev_sum = 0.f;
-            if (t > 0) {   // the previous step's cross-lane sum: its loads are in flight while this step's rings run
-                __syncwarp();
-                const float *xp = xps + ((t - 1) & 1) * G::XPOSE_PAR;
-                float part[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    part[m] = (xp[(4 * m) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 1) * G::XPOSE_STRIDE + l16]) +
-                              (xp[(4 * m + 2) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 3) * G::XPOSE_STRIDE + l16]);
-                prev_sum = (part[0] + part[1]) + (part[2] + part[3]);
-            }
-#endif
             float c[CL], pj[PL];
 #pragma unroll
             for (int v = 0; v < CL / 4; ++v)
@@ -316,13 +270,6 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                 *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
             float bx[4][4];
             ring.template step<DIR>(q, c, pj, seed, bx);
-#ifdef CUSTMA_BWD_DEFER
-            if (t > 0) {   // park the previous step's sum in its slot's staging area and release that slot
-                smem[((t - 1) & (NS - 1)) * G::SLOT + G::OFF_STG + u * 16 + l16] = prev_sum;
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&empty_bar[(t - 1) & (NS - 1)]);
-            }
-#endif
 
             float a4[4], e4[4], sp[8], ey[8];
             *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
@@ -332,13 +279,11 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
             *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
             if (MODE != 2) {
-#ifndef CUSTMA_BWD_LDG
                 asm volatile("cp.async.wait_group %0;" ::"n"(GLA) : "memory");
                 const float *gs = has_cells ? gsm + ((hr & (kGradStages - 1)) * 4) * (4 * NT) + 4 * tid : gzero;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
-#endif
                 if (MODE == 1) {   // whatever the caller left in the invalid cells of the gradient must not leak
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -356,18 +301,6 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                         gg[i][j] = valid ? __ldg(gsrc + hr * g_row + (int64_t)i * C + (p.banded ? s : d)) : 0.f;
                     }
             }
-#ifdef CUSTMA_BWD_EARLY
-            // mbarrier.try_wait takes ~90 cycles even on a completed phase: test the NEXT step's barriers now, consult the
-            // answers then
-            if (t + 1 < steps) {
-                const int tn = t + 1;
-                ready = mbar_try_wait(&full_bar[tn & (NS - 1)], (tn / NS) & 1) ? 1u : 0u;
-                if (tn >= NS - kBwdLookahead) {
-                    const int te = tn - (NS - kBwdLookahead);
-                    ready |= mbar_try_wait(&empty_bar[te & (NS - 1)], (te / NS) & 1) ? 2u : 0u;
-                }
-            }
-#endif
             float a[4][4];
             float red[16];  // T1[0..8), Bs[0..4), Am[0..4)
             if (has_cells) {
@@ -420,15 +353,6 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             }
             // ---- sum the 16 partials over the 16 lanes of the unit through a shared-memory transpose (fixed order):
             //      lane l ends with value #l
-#ifdef CUSTMA_BWD_DEFER
-            {   // summed during the next step
-                float *xw = xps + (t & 1) * G::XPOSE_PAR;
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    *reinterpret_cast<float4 *>(xw + l16 * G::XPOSE_STRIDE + 4 * v) =
-                        make_float4(red[4 * v], red[4 * v + 1], red[4 * v + 2], red[4 * v + 3]);
-            }
-#else
             {
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
@@ -444,24 +368,8 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
-#endif
         }
     }
-#ifdef CUSTMA_BWD_DEFER
-    {   // the last step's cross-lane sum
-        const int tl = steps - 1;
-        __syncwarp();
-        const float *xp = xps + (tl & 1) * G::XPOSE_PAR;
-        float part[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            part[m] = (xp[(4 * m) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 1) * G::XPOSE_STRIDE + l16]) +
-                      (xp[(4 * m + 2) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 3) * G::XPOSE_STRIDE + l16]);
-        smem[(tl & (NS - 1)) * G::SLOT + G::OFF_STG + u * 16 + l16] = (part[0] + part[1]) + (part[2] + part[3]);
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty_bar[tl & (NS - 1)]);
-    }
-#endif
     // the sums of the last steps
     for (int ts = steps - (NS - kBwdLookahead); ts < steps; ++ts) {
         if (ts < 0) continue;

@@ -75,6 +75,13 @@ uint64_t custma_launch_count(void);
  * its workspace row and 16-byte aligned, chunks covering every disparity, ...).  Needs no GPU.  0 = consistent. */
 int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size);
 
+/* Where a custma_forward call leaves its conditioning verdict (bench.py reports it): after the call, the uint32 at byte
+ * count_offset of the workspace holds the number of work items (flagged tile x 4-row groups) handed to the per-cell
+ * fallback; capacity is the number of such items in the whole call.  Above 4 % of the capacity the tensor-core kernels
+ * compute the call when tensor_core_available.  CUSTMA_ERR_UNSUPPORTED when the shape has no sliding-window kernel. */
+int custma_debug_verdict_info(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, size_t *count_offset,
+                              uint32_t *capacity, int32_t *tensor_core_available);
+
 /* Workspace (device memory, 256-byte aligned) the caller must provide; depends only on the arguments shown. */
 size_t custma_forward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
 size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
