@@ -39,6 +39,9 @@ SYMBOLS = (
     "custma_backward",
     "custma_backward_rows",
     "custma_ingest_u8",
+    "custma_head_workspace_bytes",
+    "custma_forward_head",
+    "custma_backward_head",
     "custma_host_step",
     "custma_host_submit",
     "custma_host_wait",
@@ -61,7 +64,7 @@ def _declare(lib):
     lib.custma_last_error.argtypes = []
     lib.custma_launch_count.restype = ctypes.c_uint64
     lib.custma_launch_count.argtypes = []
-    for name in ("custma_forward_workspace_bytes", "custma_backward_workspace_bytes"):
+    for name in ("custma_forward_workspace_bytes", "custma_backward_workspace_bytes", "custma_head_workspace_bytes"):
         fn = getattr(lib, name)
         fn.restype = _size
         fn.argtypes = [_i32, _i32, _i32, _i32, _i32, _u32]
@@ -80,6 +83,12 @@ def _declare(lib):
     lib.custma_backward_rows.restype = ctypes.c_int
     lib.custma_backward_rows.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32, _ptr,
                                          _size, _ptr]
+    lib.custma_forward_head.restype = ctypes.c_int
+    lib.custma_forward_head.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_float, ctypes.c_float, _i32, _i32,
+                                        _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_backward_head.restype = ctypes.c_int
+    lib.custma_backward_head.argtypes = [_ptr, _ptr, _ptr, _ptr, ctypes.c_float, _ptr, _i32, _i32, _i32, _i32, _i32, _u32,
+                                         _ptr, _size, _ptr]
     lib.custma_ingest_u8.restype = ctypes.c_int
     lib.custma_ingest_u8.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, ctypes.c_float, _ptr]
     lib.custma_host_step.restype = ctypes.c_int
@@ -167,6 +176,25 @@ def backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W,
     rc = load().custma_backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin,
                                      row_end, flags, ws_ptr or None, ws_bytes, stream or None)
     check(rc, "custma_backward_rows")
+
+
+def head_workspace_bytes(B, H, W, D, k, flags=0) -> int:
+    return int(load().custma_head_workspace_bytes(B, H, W, D, k, flags))
+
+
+def forward_head(camera_ptr, projector_ptr, soft_ptr, best_ptr, index_ptr, mask_ptr, state_ptr, beta, threshold,
+                 B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    rc = load().custma_forward_head(camera_ptr, projector_ptr, soft_ptr, best_ptr or None, index_ptr or None,
+                                    mask_ptr or None, state_ptr or None, float(beta), float(threshold), B, H, W, D, k,
+                                    flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_forward_head")
+
+
+def backward_head(soft_grad_ptr, camera_ptr, projector_ptr, state_ptr, beta, camera_grad_ptr, B, H, W, D, k, flags, ws_ptr,
+                  ws_bytes, stream):
+    rc = load().custma_backward_head(soft_grad_ptr, camera_ptr, projector_ptr, state_ptr, float(beta), camera_grad_ptr,
+                                     B, H, W, D, k, flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_backward_head")
 
 
 def ingest_u8(src_ptr, dst_ptr, B, H, W, channels, channel, scale, stream):

@@ -34,6 +34,27 @@ struct WtaExtras {
 };
 int launch_wta_extras(const Problem &p, const float *best, const int32_t *index, const WtaExtras &ex, cudaStream_t stream);
 
+// Fused differentiable disparity head (examples/verify.py:31-39 soft_argmax with beta = 50, :72-74 mask; the disparity of
+// examples/test.py:79-86): softmax over the last axis of beta * cost, soft disparity = sum_s w_s * s.  The forward kernels
+// leave one partial (m, z, n) per pixel and slot - slot = (disparity chunk, 64-disparity unit) - with m = max cost of the
+// slot's valid cells, z = sum exp(beta (c - m)), n = sum exp(beta (c - m)) * s; head_decode_kernel merges the slots.
+struct HeadOut {
+    float4 *part = nullptr;      // [slots][B*H*W]
+    int32_t slots = 0;
+    float beta_log2e = 0.f;      // beta * log2(e): exp(beta x) = exp2(beta_log2e * x)
+};
+// what the backward needs per pixel to rebuild the upstream gradient of every cell without reading a volume:
+//   g[s] = exp2(beta_log2e * c[s] - x) * (s * y - z),  x = beta_log2e * max,  y = beta * gd * mask / Z,  z = y * soft
+struct HeadGrad {
+    const float4 *state = nullptr;   // [B*H*W] (x, y, z, -); nullptr: the gradient comes from a tensor as usual
+    float beta_log2e = 0.f;
+};
+__device__ __forceinline__ float exp2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // thread-local error message storage (custma_api.cu)
 int set_error(int code, const char *fmt, ...);
 // process-wide count of kernels this library has launched (custma_launch_count)
@@ -78,6 +99,15 @@ size_t sliding_backward_workspace_bytes(const Problem &p);
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
                            int32_t *index, const WtaExtras &extras, void *workspace, size_t workspace_bytes,
                            bool force_tensor, cudaStream_t stream);
+// fused head (sliding_forward.cu): soft disparity * mask, best, index, mask, and the per-pixel state of the backward
+size_t sliding_head_forward_workspace_bytes(const Problem &p);
+int launch_sliding_forward_head(const Problem &p, const float *cam, const float *proj, float *soft_disparity, float *best,
+                                int32_t *index, float *mask, float4 *head_state, float beta, float threshold,
+                                void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t sliding_head_backward_workspace_bytes(const Problem &p);
+int launch_sliding_backward_head(const Problem &p, const float *soft_grad, const float *cam, const float *proj,
+                                 const float4 *head_state, float beta, float *camera_grad, void *workspace,
+                                 size_t workspace_bytes, cudaStream_t stream);
 // tensor-core forward (tc_forward.cu): runs when fb_count is NULL or *fb_count > threshold, writes packed WTA keys
 bool tc_forward_supported(const Problem &p);
 int launch_tc_forward(const Problem &p, const float *cam, const float *proj, float *cost, unsigned long long *keys,

@@ -234,6 +234,65 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
                          workspace, workspace_bytes, stream_);
 }
 
+// ---- fused differentiable disparity head -------------------------------------------------------
+size_t custma_head_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    Problem p;
+    if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK || (flags & (CUSTMA_FLAG_DIRECT | CUSTMA_FLAG_TENSOR))) return 0;
+    const size_t f = sliding_head_forward_workspace_bytes(p), b = sliding_head_backward_workspace_bytes(p);
+    if (f == 0 || b == 0) return 0;
+    return stats_bytes(p) + (f > b ? f : b);
+}
+
+int custma_forward_head(const float *camera, const float *projector, float *soft_disparity, float *best, int32_t *index,
+                        float *mask, float *head_state, float beta, float mask_threshold, int32_t B, int32_t H, int32_t W,
+                        int32_t D, int32_t k, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if (!camera || !projector || !soft_disparity)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera, projector and soft_disparity must not be NULL");
+    if ((best == nullptr) != (index == nullptr)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "best and index must be given together");
+    if (!(beta > 0.f) || !(beta <= 1e4f)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "beta must be in (0, 1e4], got %g", (double)beta);
+    if (flags & (CUSTMA_FLAG_DIRECT | CUSTMA_FLAG_TENSOR))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head runs on the sliding-window kernels only (no CUSTMA_FLAG_DIRECT / CUSTMA_FLAG_TENSOR)");
+    if (head_state && ((uintptr_t)head_state & 15u)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "head_state must be 16-byte aligned");
+    if ((rc = check_image_alignment(camera, "camera")) || (rc = check_image_alignment(projector, "projector")) ||
+        (rc = check_image_alignment(soft_disparity, "soft_disparity")) || (rc = check_image_alignment(best, "best")) ||
+        (rc = check_image_alignment(index, "index")) || (rc = check_image_alignment(mask, "mask")))
+        return rc;
+    if ((rc = check_device())) return rc;
+    const size_t need = custma_head_workspace_bytes(B, H, W, D, k, flags);
+    if (need == 0) return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head needs kernel_size 3 or 5 (forward and backward fast paths), got %d", k);
+    StatsPtrs s;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, need, &s))) return rc;
+    return launch_sliding_forward_head(p, camera, projector, soft_disparity, best, index, mask, (float4 *)head_state, beta,
+                                       mask_threshold, s.rest, s.rest_bytes, (cudaStream_t)stream_);
+}
+
+int custma_backward_head(const float *soft_disparity_grad, const float *camera, const float *projector,
+                         const float *head_state, float beta, float *camera_grad, int32_t B, int32_t H, int32_t W, int32_t D,
+                         int32_t k, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if (!soft_disparity_grad || !camera || !projector || !head_state || !camera_grad)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "soft_disparity_grad, camera, projector, head_state and camera_grad must not be NULL");
+    if (!(beta > 0.f) || !(beta <= 1e4f)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "beta must be in (0, 1e4], got %g", (double)beta);
+    if (flags & (CUSTMA_FLAG_DIRECT | CUSTMA_FLAG_TENSOR))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head runs on the sliding-window kernels only (no CUSTMA_FLAG_DIRECT / CUSTMA_FLAG_TENSOR)");
+    if ((uintptr_t)head_state & 15u) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "head_state must be 16-byte aligned");
+    if ((rc = check_image_alignment(camera, "camera")) || (rc = check_image_alignment(projector, "projector")) ||
+        (rc = check_image_alignment(soft_disparity_grad, "soft_disparity_grad")) || (rc = check_image_alignment(camera_grad, "camera_grad")))
+        return rc;
+    if ((rc = check_device())) return rc;
+    const size_t need = custma_head_workspace_bytes(B, H, W, D, k, flags);
+    if (need == 0) return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head needs kernel_size 3 or 5, got %d", k);
+    StatsPtrs s;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, need, &s))) return rc;
+    return launch_sliding_backward_head(p, soft_disparity_grad, camera, projector, (const float4 *)head_state, beta,
+                                        camera_grad, s.rest, s.rest_bytes, (cudaStream_t)stream_);
+}
+
 // uint8 ingestion (examples/verify.py:138-142,149: cv2.imread(...) / 255, channel 0 of the RGB image): one pass from the
 // interleaved 8-bit image to the fp32 plane the kernels read
 __global__ void __launch_bounds__(256)

@@ -155,12 +155,14 @@ struct SumRing {
     }
 };
 
-template <int K, int NU, int WG, int MODE, int DIR>
+// HG: the upstream gradient of a cell is rebuilt from the fused head's per-pixel state (HeadGrad, common.cuh) instead of
+// being read from a [.., C] tensor: the "gradient row" the ring prefetches is then one float4 per camera column.
+template <int K, int NU, int WG, int MODE, int DIR, bool HG>
 __device__ __forceinline__ void backward_consumer(const Problem &p, const SlidingLayout &L, float *smem,
                                                   uint64_t *full_bar, uint64_t *empty_bar,
                                                   BwdRowLoader<K, NU, WG> &loader, int b, int h0, int rows, int w_base,
                                                   int s_base, int steps, const float *__restrict__ grad,
-                                                  float *__restrict__ T1tile, int T1pitch,
+                                                  const HeadGrad &hg, float *__restrict__ T1tile, int T1pitch,
                                                   float *__restrict__ AmRow, float *__restrict__ BsRow) {
     using F = SlideGeom<K, NU, WG>;
     using G = BwdGeom<K, NU, WG>;
@@ -176,8 +178,9 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
     float *gsm = smem + NS * G::SLOT;   // [kGradStages][4][NT] float4
     // upstream gradient of (row h0, column w0, disparity s0); row hr, column i: + (hr*W + i) * C
     // (the gradient buffer holds volume rows [p.g0, p.g1) only: custma_backward_rows)
-    const float *gsrc = grad + (((int64_t)b * p.grows() + (h0 - p.g0)) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
-    const int g_lo = max(0, p.g0 - h0), g_hi = min(rows, p.g1 - h0);   // band rows that carry a gradient
+    const float *gsrc = HG ? reinterpret_cast<const float *>(hg.state) + (((int64_t)b * p.H + h0) * p.W + w0) * 4
+                           : grad + (((int64_t)b * p.grows() + (h0 - p.g0)) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
+    const int g_lo = HG ? 0 : max(0, p.g0 - h0), g_hi = HG ? rows : min(rows, p.g1 - h0);   // band rows that carry a gradient
     uint32_t cmask = 0;  // MODE 1: bit 4i+j = cell (w0+i, s0+j) exists and is valid; constant over the band's rows
     if (MODE == 1) {
 #pragma unroll
@@ -186,7 +189,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
             for (int j = 0; j < 4; ++j)
                 if (w0 + i < p.W && w0 + i - (s0 + j) >= 0) cmask |= 1u << (4 * i + j);
     }
-    const int64_t g_row = (int64_t)p.W * C;
+    const int64_t g_row = HG ? (int64_t)p.W * 4 : (int64_t)p.W * C, g_col = HG ? 4 : C;
 
     float *xps = gsm + G::GRAD_FLOATS + u * G::XPOSE_UNIT;   // this unit's transpose scratch
     const float *gzero = gsm + (kGradStages * 4) * (4 * NT) + 4 * tid;  // a stage that is never written: stays zero
@@ -251,7 +254,7 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (MODE == 0 || w0 + i < p.W)   // columns past the image stay zero from the initial fill
-                            cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * C);
+                            cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * g_col);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
@@ -284,12 +287,19 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
-                if (MODE == 1) {   // whatever the caller left in the invalid cells of the gradient must not leak
+                if (MODE == 1 && !HG) {   // whatever the caller left in the invalid cells of the gradient must not leak
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (!((cmask >> (4 * i + j)) & 1u)) gg[i][j] = 0.f;
+                }
+            } else if (HG) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_cells && w0 + i < p.W) st = __ldg(reinterpret_cast<const float4 *>(gsrc + hr * g_row + (int64_t)i * 4));
+                    gg[i][0] = st.x; gg[i][1] = st.y; gg[i][2] = st.z; gg[i][3] = st.w;
                 }
             } else {
 #pragma unroll
@@ -312,7 +322,18 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
                         const int di = i - j + 3;
                         const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
                         const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
-                        const float av = gg[i][j] * rs;                              // a  = g / den               (:135,:145)
+                        float g = gg[i][j];
+                        if (HG) {   // softmax weight of the cell times (s - soft disparity), scaled per pixel (HeadGrad)
+                            g = exp2_fast(fmaf(e * rs, hg.beta_log2e, -gg[i][0])) * fmaf((float)(s0 + j), gg[i][1], -gg[i][2]);
+                            bool valid = true;
+                            if (MODE == 1) valid = (cmask >> (4 * i + j)) & 1u;
+                            if (MODE == 2) {
+                                const int d = w0 + i - (s0 + j);
+                                valid = w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
+                            }
+                            g = valid ? g : 0.f;
+                        }
+                        const float av = g * rs;                                     // a  = g / den               (:135,:145)
                         a[i][j] = av;                                                // bc = g*ey2*(exy+eps)/den^3 (:147)
                         bs = j == 0 ? (av * e) * (ey[di] * (rs * rs)) : fmaf(av * e, ey[di] * (rs * rs), bs);
                         am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
@@ -379,10 +400,10 @@ __device__ __forceinline__ void backward_consumer(const Problem &p, const Slidin
 }
 
 
-template <int K, int NU, int WG>
+template <int K, int NU, int WG, bool HG>
 __global__ void __launch_bounds__(16 * NU * WG, 1)
     sliding_backward_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
-                            const float *__restrict__ grad, const uint32_t tc_threshold) {
+                            const float *__restrict__ grad, const uint32_t tc_threshold, const HeadGrad hg) {
     using F = SlideGeom<K, NU, WG>;
     constexpr int WTC = F::WTC, SC = F::SC, NS = F::NS, NCW = F::NCW;
     extern __shared__ __align__(128) float smem[];
@@ -434,8 +455,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 1)
     const bool clean_left = w_base > 0 && w_base - (s_base + SC - 1) - (K / 2 + 3) >= 0;
     const bool clean_right = w_base + WTC + K <= p.W;
 #define CUSTMA_BWD_BODY(MODE, DIR)                                                                                      \
-    backward_consumer<K, NU, WG, MODE, DIR>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base, steps, \
-                                            grad, T1tile, BL.Wp, AmRow, BsRow)
+    backward_consumer<K, NU, WG, MODE, DIR, HG>(p, L, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,  \
+                                                steps, grad, hg, T1tile, BL.Wp, AmRow, BsRow)
     if (vec && clean_left && w_base + WTC <= p.W) CUSTMA_BWD_BODY(0, 1);
     else if (vec && clean_right) CUSTMA_BWD_BODY(1, 2);
     else if (vec) CUSTMA_BWD_BODY(1, 0);
@@ -593,24 +614,24 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
 
 template <int K, int NU, int WG>
 static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws, const float *grad,
-                          uint32_t thr, cudaStream_t stream) {
+                          uint32_t thr, const HeadGrad &hg, cudaStream_t stream) {
     const size_t smem = BwdGeom<K, NU, WG>::SMEM_BYTES;
-    auto kern = sliding_backward_kernel<K, NU, WG>;
+    auto kern = hg.state ? sliding_backward_kernel<K, NU, WG, true> : sliding_backward_kernel<K, NU, WG, false>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad, thr);
+    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad, thr, hg);
     CUSTMA_LAUNCH_CHECK("sliding_backward_kernel");
     return CUSTMA_OK;
 }
 
 template <int K>
 static int launch_bwd_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws,
-                        const float *grad, uint32_t thr, cudaStream_t stream) {
+                        const float *grad, uint32_t thr, const HeadGrad &hg, cudaStream_t stream) {
     switch (cfg.NU) {
-        case 1: return launch_bwd_cfg<K, 1, 16>(p, L, BL, ws, grad, thr, stream);
-        case 2: return launch_bwd_cfg<K, 2, 8>(p, L, BL, ws, grad, thr, stream);
-        case 3: return launch_bwd_cfg<K, 3, 5>(p, L, BL, ws, grad, thr, stream);
-        default: return launch_bwd_cfg<K, 4, 4>(p, L, BL, ws, grad, thr, stream);
+        case 1: return launch_bwd_cfg<K, 1, 16>(p, L, BL, ws, grad, thr, hg, stream);
+        case 2: return launch_bwd_cfg<K, 2, 8>(p, L, BL, ws, grad, thr, hg, stream);
+        case 3: return launch_bwd_cfg<K, 3, 5>(p, L, BL, ws, grad, thr, hg, stream);
+        default: return launch_bwd_cfg<K, 4, 4>(p, L, BL, ws, grad, thr, hg, stream);
     }
 }
 
@@ -654,15 +675,73 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     // computes the whole call and the sliding / fallback / finalize kernels return at once
     const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;
     const uint32_t thr = tc_backward_supported(p) ? (uint32_t)(0.04 * items) : 0xffffffffu;
-    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, thr, stream) : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, thr, stream);
+    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, grad, thr, HeadGrad(), stream)
+                  : launch_bwd_k<5>(cfg, p, L, BL, ws, grad, thr, HeadGrad(), stream);
     if (rc) return rc;
-    if ((rc = launch_fallback_patch_grad(p, L, grad, cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
+    if ((rc = launch_fallback_patch_grad(p, L, grad, HeadGrad(), cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
     const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinRows - 1) / kFinRows, p.B), fblock(kFinTX, kFinTY);
     if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     if (thr != 0xffffffffu)
         return launch_tc_backward(p, grad, cam, proj, camera_grad, tc_scratch, (const uint32_t *)(ws + L.off_fb_count), thr, stream);
+    return CUSTMA_OK;
+}
+
+// ---- fused head: backward without a volume ---------------------------------------------------------------------
+// per pixel: (x, y, z, -) = (beta_log2e * max, beta * gd * mask / Z, y * soft, -) from the forward's state and the upstream
+// gradient gd of the masked soft disparity; every cell's gradient is then exp2(beta_log2e * c - x) * (s * y - z)
+__global__ void __launch_bounds__(256)
+    head_grad_prep_kernel(int64_t pixels, const float4 *__restrict__ state, const float *__restrict__ soft_grad, float beta,
+                          float4 *__restrict__ out) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= pixels) return;
+    const float4 st = state[pix];                      // (beta_log2e * M, 1 / Z, soft, mask)
+    const float y = beta * soft_grad[pix] * st.w * st.y;
+    out[pix] = make_float4(st.x, y, y * st.z, 0.f);
+}
+
+size_t sliding_head_backward_workspace_bytes(const Problem &p) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, true, &cfg)) return 0;
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, true, &L);
+    BwdLayout BL;
+    make_bwd_layout(p, L, &BL);
+    return align256(BL.total) + align256((size_t)p.pixels() * sizeof(float4));
+}
+
+int launch_sliding_backward_head(const Problem &p, const float *soft_grad, const float *cam, const float *proj,
+                                 const float4 *head_state, float beta, float *camera_grad, void *workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, true, &cfg))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head's backward needs kernel_size 3 or 5, got %d", p.k);
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, true, &L);
+    BwdLayout BL;
+    make_bwd_layout(p, L, &BL);
+    const size_t need = align256(BL.total) + align256((size_t)p.pixels() * sizeof(float4));
+    if (workspace_bytes < need)
+        return set_error(CUSTMA_ERR_WORKSPACE, "fused head backward needs %zu workspace bytes, %zu given", need, workspace_bytes);
+    char *ws = (char *)workspace;
+    float4 *hs = (float4 *)(ws + align256(BL.total));
+    head_grad_prep_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p.pixels(), head_state, soft_grad, beta, hs);
+    CUSTMA_LAUNCH_CHECK("head_grad_prep_kernel");
+    HeadGrad hg;
+    hg.state = hs;
+    hg.beta_log2e = beta * 1.4426950408889634f;
+    int rc = launch_sliding_prep(p, L, cam, proj, ws, stream);
+    if (rc) return rc;
+    const uint32_t thr = 0xffffffffu;   // flagged tiles go to the per-cell fallback (the tensor-core kernel reads a volume)
+    rc = p.k == 3 ? launch_bwd_k<3>(cfg, p, L, BL, ws, nullptr, thr, hg, stream)
+                  : launch_bwd_k<5>(cfg, p, L, BL, ws, nullptr, thr, hg, stream);
+    if (rc) return rc;
+    if ((rc = launch_fallback_patch_grad(p, L, nullptr, hg, cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
+    const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinRows - 1) / kFinRows, p.B), fblock(kFinTX, kFinTY);
+    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;
 }
 

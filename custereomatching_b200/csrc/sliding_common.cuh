@@ -281,10 +281,10 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
                         cudaStream_t stream);
 // sliding_fallback.cu: the flagged tiles, cell by cell in the reference's arithmetic
 int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
-                            const char *ws, float *cost, unsigned long long *keys, uint32_t tc_threshold,
-                            cudaStream_t stream);
-int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
-                               const float *proj, const char *ws, float *patch_grad, uint32_t tc_threshold,
-                               cudaStream_t stream);
+                            const char *ws, float *cost, unsigned long long *keys, const HeadOut &head,
+                            uint32_t tc_threshold, cudaStream_t stream);
+int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const HeadGrad &hg,
+                               const float *cam, const float *proj, const char *ws, float *patch_grad,
+                               uint32_t tc_threshold, cudaStream_t stream);
 
 }  // namespace custma

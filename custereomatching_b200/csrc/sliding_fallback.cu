@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                             const float *__restrict__ proj, const uint8_t *__restrict__ flags,
                             const uint32_t *__restrict__ fb_count, const uint32_t *__restrict__ fb_list,
                             const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
-                            float *__restrict__ cost, unsigned long long *__restrict__ keys, const uint32_t tc_threshold) {
+                            float *__restrict__ cost, unsigned long long *__restrict__ keys, const uint32_t tc_threshold,
+                            const HeadOut head) {
     extern __shared__ float smem[];
     const uint32_t n_items = *fb_count;
     if (n_items > tc_threshold) return;   // so much is flagged that the tensor-core kernel computes the whole call
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(kFbWarps * 32)
     const int h0 = nb * L.RB + rg * kFbRows, w_base = wt * L.WTC;
     const int rows = min(min(kFbRows, L.RB - rg * kFbRows), p.H - h0), cols = min(L.WTC, p.W - w_base);
     const float *cam_plane = cam + (int64_t)b * p.H * p.W, *proj_plane = proj + (int64_t)b * p.H * p.W;
-    float *camc = smem + warp * p.k * p.k;
+    float *camc = smem + warp * (p.k * p.k + (head.part ? p.C : 0));
+    float *vst = camc + p.k * p.k;     // head: the costs of this pixel's flagged cells (-inf where there is none)
     for (int pi = warp; pi < rows * cols; pi += kFbWarps) {
         const int h = h0 + pi / cols, w = w_base + pi % cols;
         const int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
@@ -110,7 +112,10 @@ __global__ void __launch_bounds__(kFbWarps * 32)
         float bv = -INFINITY;
         int bs = 0;
         for (int c = lane; c < p.C; c += 32) {
-            if (!fl[cell_chunk(p, L, w_base, w, c)]) continue;
+            if (!fl[cell_chunk(p, L, w_base, w, c)]) {
+                if (head.part) vst[c] = -INFINITY;
+                continue;
+            }
             const int d = p.banded ? w - c : c;
             float v = kInvalid;
             if (d >= 0) {
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                 if (v > bv || (v == bv && s > bs)) { bv = v; bs = s; }
             }
             if (cost) cost[pix * p.C + c] = v;
+            if (head.part) vst[c] = d >= 0 ? v : -INFINITY;
         }
         if (keys) {
 #pragma unroll
@@ -132,13 +138,44 @@ __global__ void __launch_bounds__(kFbWarps * 32)
             if (lane == 0 && bv > -INFINITY)
                 atomicMax(keys + pix, ((unsigned long long)float_to_ordered(bv) << 32) | (uint32_t)(bs + p.W));
         }
+        if (head.part) {
+            // softmax partial of ALL flagged cells of this pixel relative to their maximum bv (every lane holds it after
+            // the reduction above); it goes to the first slot of the first flagged chunk, the other slots of the flagged
+            // chunks are marked empty - the sliding kernel writes the slots of the chunks it keeps
+            __syncwarp();
+            float z = 0.f, n = 0.f;
+            for (int c = lane; c < p.C; c += 32) {
+                const float v = vst[c];
+                if (v > -INFINITY) {
+                    const float ex = exp2_fast(head.beta_log2e * (v - bv));
+                    z += ex;
+                    n = fmaf(ex, (float)(p.banded ? c : w - c), n);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+                n += __shfl_xor_sync(0xffffffffu, n, o);
+            }
+            if (lane == 0) {
+                bool first = true;
+                for (int ch = 0; ch < L.n_chunks; ++ch) {
+                    if (!fl[ch]) continue;
+                    for (int un = 0; un < L.NU; ++un) {
+                        head.part[(int64_t)(ch * L.NU + un) * p.pixels() + pix] =
+                            first ? make_float4(bv, z, n, 0.f) : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+                        first = false;
+                    }
+                }
+            }
+        }
     }
     }   // work items
 }
 
 // patch gradient (k*k values per pixel) of the flagged cells; layout and formula of direct_patch_grad_kernel
 __global__ void __launch_bounds__(kFbWarps * 32)
-    fallback_patch_grad_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ grad,
+    fallback_patch_grad_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ grad, const HeadGrad hg,
                                const float *__restrict__ cam, const float *__restrict__ proj,
                                const uint8_t *__restrict__ flags, const uint32_t *__restrict__ fb_count,
                                const uint32_t *__restrict__ fb_list, const float *__restrict__ fb_pm,
@@ -173,7 +210,14 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                 const float ey2 = fb_ey2[o];
                 const float exy = cell_exy(p, proj_plane, camc, h, d, pm);
                 const float den = sqrtf(fmaf(ex2, ey2, kEps));
-                const float g = (h >= p.g0 && h < p.g1) ? grad[(((int64_t)b * p.grows() + (h - p.g0)) * p.W + w) * p.C + c] : 0.f;
+                float g;
+                if (hg.state) {   // fused head: the cell's upstream gradient from the per-pixel softmax state
+                    const float4 st = hg.state[pix];
+                    const float cv = (exy + kEps) / den;
+                    g = exp2_fast(fmaf(cv, hg.beta_log2e, -st.x)) * fmaf((float)(p.banded ? c : w - c), st.y, -st.z);
+                } else {
+                    g = (h >= p.g0 && h < p.g1) ? grad[(((int64_t)b * p.grows() + (h - p.g0)) * p.W + w) * p.C + c] : 0.f;
+                }
                 a = g / den;                                          // reference :135,:145
                 bsum += g * ey2 * (exy + kEps) / (den * den * den);   // reference :147
             }
@@ -214,24 +258,28 @@ static int launch_fallback_proj_stats(const Problem &p, const SlidingLayout &L, 
 }
 
 int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const float *cam, const float *proj,
-                            const char *ws, float *cost, unsigned long long *keys, uint32_t tc_threshold,
-                            cudaStream_t stream) {
+                            const char *ws, float *cost, unsigned long long *keys, const HeadOut &head,
+                            uint32_t tc_threshold, cudaStream_t stream) {
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
-    const size_t smem = (size_t)kFbWarps * p.k * p.k * sizeof(float);
+    const size_t smem = (size_t)kFbWarps * (p.k * p.k + (head.part ? p.C : 0)) * sizeof(float);
+    if (smem > 200 * 1024)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback forward: last axis %d too long for shared memory", p.C);
+    if (smem > 48 * 1024)
+        CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(fallback_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fallback_forward_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
         p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost,
-        keys, tc_threshold);
+        keys, tc_threshold, head);
     CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
     return CUSTMA_OK;
 }
 
 size_t fallback_backward_smem(const Problem &p) { return (size_t)kFbWarps * (p.k * p.k + 2 * p.C) * sizeof(float); }
 
-int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const float *cam,
-                               const float *proj, const char *ws, float *patch_grad, uint32_t tc_threshold,
-                               cudaStream_t stream) {
+int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const float *grad, const HeadGrad &hg,
+                               const float *cam, const float *proj, const char *ws, float *patch_grad,
+                               uint32_t tc_threshold, cudaStream_t stream) {
     const size_t smem = fallback_backward_smem(p);
     if (smem > 200 * 1024)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback backward: last axis %d too long for shared memory", p.C);
@@ -240,7 +288,7 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
     fallback_patch_grad_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
-        p, L, grad, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
+        p, L, grad, hg, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2),
         patch_grad, tc_threshold);
     CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");

@@ -20,17 +20,19 @@ namespace custma {
 
 
 
-template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA, bool HEAD>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
-                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys);
+                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys,
+                                                 const HeadOut &head, int head_slot);
 
 
-template <int K, int NU, int WG, bool COST, bool WTA>
+template <int K, int NU, int WG, bool COST, bool WTA, bool HEAD>
 __global__ void __launch_bounds__(16 * NU * WG, 2)
     sliding_forward_kernel(const Problem p, const SlidingLayout L, const char *__restrict__ ws,
-                           float *__restrict__ cost, unsigned long long *__restrict__ wta_keys, const uint32_t tc_threshold) {
+                           float *__restrict__ cost, unsigned long long *__restrict__ wta_keys, const uint32_t tc_threshold,
+                           const HeadOut head) {
     using G = SlideGeom<K, NU, WG>;
     constexpr int WTC = G::WTC, SC = G::SC, NS = G::NS, NCW = G::NCW;
     extern __shared__ __align__(128) float smem[];
@@ -68,8 +70,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     const bool clean_left = w_base > 0 && w_base - (s_base + SC - 1) - (K / 2 + 3) >= 0;   // no padding left of any chain
     const bool clean_right = w_base + WTC + K <= p.W;
 #define CUSTMA_FWD_BODY(MODE, DIR)                                                                                        \
-    forward_consumer<K, NU, WG, MODE, DIR, COST, WTA>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base, s_base,  \
-                                                      steps, cost, wta_keys)
+    forward_consumer<K, NU, WG, MODE, DIR, COST, WTA, HEAD>(p, smem, full_bar, empty_bar, loader, b, h0, rows, w_base,    \
+                                                            s_base, steps, cost, wta_keys, head, ch * NU)
     if (vec && clean_left && w_base + WTC <= p.W) CUSTMA_FWD_BODY(0, 1);
     else if (vec && clean_right) CUSTMA_FWD_BODY(1, 2);
     else if (vec) CUSTMA_FWD_BODY(1, 0);
@@ -82,11 +84,13 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 __device__ __forceinline__ unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA>
+template <int K, int NU, int WG, int MODE, int DIR, bool COST, bool WTA, bool HEAD>
 __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, uint64_t *full_bar,
                                                  uint64_t *empty_bar, RowLoader<K, NU, WG> &loader, int b,
                                                  int h0, int rows, int w_base, int s_base, int steps,
-                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys) {
+                                                 float *__restrict__ cost, unsigned long long *__restrict__ wta_keys,
+                                                 const HeadOut &head, int head_slot) {
+    static_assert(!HEAD || WTA, "the head needs the unit maxima of the winner-take-all reduction");
     using G = SlideGeom<K, NU, WG>;
     constexpr int CL = G::CL, PL = G::PL, NS = G::NS, PERIOD = G::PERIOD;
     const int tid = threadIdx.x;
@@ -106,6 +110,8 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                 if (w0 + i < p.W && w0 + i - (s0 + j) >= 0) cmask |= 1u << (4 * i + j);
     }
     unsigned long long *keys = WTA ? wta_keys + pix_start : nullptr;
+    // head: this unit's slot of the partial (m, z, n) image; same running row pointer as the keys
+    float4 *hpart = HEAD ? head.part + (int64_t)(head_slot + su) * p.pixels() + pix_start : nullptr;
     const int64_t out_row = (int64_t)p.W * C;
     const float seed = kEps / (float)K;
 
@@ -140,6 +146,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                 *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
                 const bool row_ok = t - (K - 1) < rows;   // false only in the padding steps of a short last band
                 unsigned long long key[4];
+                float hv[HEAD ? 4 : 1][4];   // head: the costs of the thread's cells, -inf where no cell exists
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float v[4];
@@ -152,6 +159,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                         const float val = exy * rsqrt_fast(fmaf(e4[i], ey[di], kEps));    // reference kernel.cu:71
                         if (MODE == 0) {
                             v[j] = val;
+                            if (HEAD) hv[i][j] = val;
                             if (WTA && (j == 0 || val >= bv)) { bv = val; bs = s0 + j; }
                         } else {
                             bool valid;
@@ -162,6 +170,7 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                                 valid = d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
                             }
                             v[j] = valid ? val : kInvalid;
+                            if (HEAD) hv[i][j] = valid ? val : -INFINITY;
                             if (WTA && valid && val >= bv) { bv = val; bs = s0 + j; }
                         }
                     }
@@ -199,10 +208,47 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
                     kk = max_u64(kk, shfl_xor_u64(kk, 1));
                     const int i = (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
                     if ((l16 & 3) == 0 && row_ok && (MODE == 0 || (kk != 0ull && w0 + i < p.W))) atomicMax(keys + i, kk);
+                    if (HEAD) {
+                        // softmax partials relative to the unit's own maximum of every column: lanes 4i .. 4i+3 of the
+                        // unit hold column i's maximum after the reduce-scatter above
+                        const float kmax = kk != 0ull ? ordered_to_float((uint32_t)(kk >> 32)) : -INFINITY;
+                        float z[4], n[4];
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float m = __shfl_sync(0xffffffffu, kmax, (tid & 16) | (4 * c4));
+                            const float off = -head.beta_log2e * m;
+                            float zz = 0.f, nn = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                // exp2(-inf) = 0 for cells that do not exist; a unit without any cell has m = -inf and
+                                // only such cells (the select keeps inf - inf out of the sums)
+                                const float ex = hv[c4][j] > -INFINITY ? exp2_fast(fmaf(hv[c4][j], head.beta_log2e, off)) : 0.f;
+                                zz += ex;
+                                nn = fmaf(ex, (float)(s0 + j), nn);
+                            }
+                            z[c4] = zz;
+                            n[c4] = nn;
+                        }
+                        // sum over the 16 lanes, same reduce-scatter (fixed order: deterministic)
+                        float a0 = hi8 ? z[2] : z[0], a1 = hi8 ? z[3] : z[1], b0 = hi8 ? n[2] : n[0], b1 = hi8 ? n[3] : n[1];
+                        a0 += __shfl_xor_sync(0xffffffffu, hi8 ? z[0] : z[2], 8);
+                        a1 += __shfl_xor_sync(0xffffffffu, hi8 ? z[1] : z[3], 8);
+                        b0 += __shfl_xor_sync(0xffffffffu, hi8 ? n[0] : n[2], 8);
+                        b1 += __shfl_xor_sync(0xffffffffu, hi8 ? n[1] : n[3], 8);
+                        float zs = (hi4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi4 ? a0 : a1, 4);
+                        float ns = (hi4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, hi4 ? b0 : b1, 4);
+                        zs += __shfl_xor_sync(0xffffffffu, zs, 2);
+                        ns += __shfl_xor_sync(0xffffffffu, ns, 2);
+                        zs += __shfl_xor_sync(0xffffffffu, zs, 1);
+                        ns += __shfl_xor_sync(0xffffffffu, ns, 1);
+                        if ((l16 & 3) == 0 && row_ok && (MODE == 0 || w0 + i < p.W))
+                            hpart[i] = make_float4(kmax, zs, ns, 0.f);
+                    }
                 }
             }
             if (COST) out += out_row;
             if (WTA) keys += p.W;
+            if (HEAD) hpart += p.W;
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[slot]);
         }
@@ -238,6 +284,40 @@ __global__ void __launch_bounds__(256)
     if (ex.masked_disparity) ex.masked_disparity[pix] = (float)(p.banded ? idx : (int)(pix % p.W) - idx) * m;
 }
 
+// Merges the head's per-slot partials of a pixel: M = max m, Z = sum z * exp(beta (m - M)), N likewise; soft disparity
+// N / Z (examples/verify.py:31-39 on the disparity axis; for the reference-shaped volume s = column - correspondence runs
+// over every projector column, so N / Z = column - soft correspondence, examples/test.py:85).  Writes the masked soft
+// disparity (test.py:86), best / index / mask as wta_decode_kernel does, and the state the backward needs.
+__global__ void __launch_bounds__(256)
+    head_decode_kernel(Problem p, const unsigned long long *__restrict__ keys, const HeadOut head,
+                       float *__restrict__ soft, float *__restrict__ best, int32_t *__restrict__ index,
+                       float *__restrict__ mask, float4 *__restrict__ state, float threshold) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.pixels()) return;
+    float M = -INFINITY;
+    for (int sl = 0; sl < head.slots; ++sl) M = fmaxf(M, head.part[(int64_t)sl * p.pixels() + pix].x);
+    float Z = 0.f, N = 0.f;
+    for (int sl = 0; sl < head.slots; ++sl) {
+        const float4 q = head.part[(int64_t)sl * p.pixels() + pix];
+        if (q.x > -INFINITY) {
+            const float w = exp2_fast(head.beta_log2e * (q.x - M));
+            Z = fmaf(q.y, w, Z);
+            N = fmaf(q.z, w, N);
+        }
+    }
+    const float sd = N / Z;                       // Z >= 1: the winning cell contributes exp(0)
+    const float m = M > threshold ? 1.f : 0.f;
+    soft[pix] = sd * m;
+    if (mask) mask[pix] = m;
+    if (best) {
+        const unsigned long long key = keys[pix];
+        const int s = (int)(uint32_t)(key & 0xffffffffu) - p.W;
+        best[pix] = ordered_to_float((uint32_t)(key >> 32));
+        index[pix] = p.banded ? s : (int)(pix % p.W) - s;
+    }
+    if (state) state[pix] = make_float4(head.beta_log2e * M, 1.f / Z, sd, m);
+}
+
 int launch_wta_extras(const Problem &p, const float *best, const int32_t *index, const WtaExtras &ex, cudaStream_t stream) {
     if (!ex.mask && !ex.masked_disparity) return CUSTMA_OK;
     wta_extras_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, best, index, ex);
@@ -245,35 +325,36 @@ int launch_wta_extras(const Problem &p, const float *best, const int32_t *index,
     return CUSTMA_OK;
 }
 
-template <int K, int NU, int WG, bool COST, bool WTA>
+template <int K, int NU, int WG, bool COST, bool WTA, bool HEAD>
 static int launch_one(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                      unsigned long long *keys, uint32_t tc_threshold, cudaStream_t stream) {
+                      unsigned long long *keys, uint32_t tc_threshold, const HeadOut &head, cudaStream_t stream) {
     const size_t smem = (size_t)kSlidingStages * SlideGeom<K, NU, WG>::SLOT * sizeof(float);
     const int threads = 16 * NU * WG;
-    auto kern = sliding_forward_kernel<K, NU, WG, COST, WTA>;
+    auto kern = sliding_forward_kernel<K, NU, WG, COST, WTA, HEAD>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys, tc_threshold);
+    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys, tc_threshold, head);
     CUSTMA_LAUNCH_CHECK("sliding_forward_kernel");
     return CUSTMA_OK;
 }
 
 template <int K, int NU, int WG>
 static int launch_cfg(const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                      unsigned long long *keys, uint32_t thr, cudaStream_t stream) {
-    if (cost && keys) return launch_one<K, NU, WG, true, true>(p, L, ws, cost, keys, thr, stream);
-    if (cost) return launch_one<K, NU, WG, true, false>(p, L, ws, cost, keys, thr, stream);
-    return launch_one<K, NU, WG, false, true>(p, L, ws, cost, keys, thr, stream);
+                      unsigned long long *keys, uint32_t thr, const HeadOut &head, cudaStream_t stream) {
+    if (head.part) return launch_one<K, NU, WG, false, true, true>(p, L, ws, nullptr, keys, thr, head, stream);
+    if (cost && keys) return launch_one<K, NU, WG, true, true, false>(p, L, ws, cost, keys, thr, head, stream);
+    if (cost) return launch_one<K, NU, WG, true, false, false>(p, L, ws, cost, keys, thr, head, stream);
+    return launch_one<K, NU, WG, false, true, false>(p, L, ws, cost, keys, thr, head, stream);
 }
 
 template <int K>
 static int launch_k(const SlidingConfig &cfg, const Problem &p, const SlidingLayout &L, const char *ws, float *cost,
-                    unsigned long long *keys, uint32_t thr, cudaStream_t stream) {
+                    unsigned long long *keys, uint32_t thr, const HeadOut &head, cudaStream_t stream) {
     switch (cfg.NU) {
-        case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, thr, stream);
-        case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, thr, stream);
-        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, thr, stream);
-        default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, thr, stream);
+        case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, thr, head, stream);
+        case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, thr, head, stream);
+        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, thr, head, stream);
+        default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, thr, head, stream);
     }
 }
 
@@ -315,11 +396,11 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
         if ((rc = launch_sliding_prep(p, L, cam, proj, ws, stream))) return rc;
         const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;
         const uint32_t thr = tc_forward_supported(p) ? (uint32_t)(kTensorShare * items) : 0xffffffffu;
-        rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, thr, stream)
-           : p.k == 5 ? launch_k<5>(cfg, p, L, ws, cost, keys, thr, stream)
-                      : launch_k<7>(cfg, p, L, ws, cost, keys, thr, stream);
+        rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, thr, HeadOut(), stream)
+           : p.k == 5 ? launch_k<5>(cfg, p, L, ws, cost, keys, thr, HeadOut(), stream)
+                      : launch_k<7>(cfg, p, L, ws, cost, keys, thr, HeadOut(), stream);
         if (rc) return rc;
-        if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, thr, stream))) return rc;
+        if ((rc = launch_fallback_forward(p, L, cam, proj, ws, cost, keys, HeadOut(), thr, stream))) return rc;
         if (thr != 0xffffffffu &&
             (rc = launch_tc_forward(p, cam, proj, cost, keys, (const uint32_t *)(ws + L.off_fb_count), thr, stream)))
             return rc;
@@ -328,6 +409,52 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
         wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index, extras);
         CUSTMA_LAUNCH_CHECK("wta_decode_kernel");
     }
+    return CUSTMA_OK;
+}
+
+// ---- fused head ------------------------------------------------------------------------------------------------
+static size_t head_part_bytes(const Problem &p, const SlidingLayout &L) {
+    return align256((size_t)L.n_chunks * L.NU * p.pixels() * sizeof(float4));
+}
+
+size_t sliding_head_forward_workspace_bytes(const Problem &p) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, false, &cfg)) return 0;
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, false, &L);
+    return align256(L.total) + head_part_bytes(p, L);
+}
+
+int launch_sliding_forward_head(const Problem &p, const float *cam, const float *proj, float *soft_disparity, float *best,
+                                int32_t *index, float *mask, float4 *head_state, float beta, float threshold,
+                                void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    SlidingConfig cfg;
+    if (!sliding_pick_config(p, false, &cfg))
+        return set_error(CUSTMA_ERR_UNSUPPORTED, "the fused head needs a sliding-window kernel: kernel_size 3, 5 or 7, got %d", p.k);
+    SlidingLayout L;
+    make_sliding_layout(p, cfg, false, &L);
+    const size_t need = align256(L.total) + head_part_bytes(p, L);
+    if (workspace_bytes < need)
+        return set_error(CUSTMA_ERR_WORKSPACE, "fused head forward needs %zu workspace bytes, %zu given", need, workspace_bytes);
+    char *ws = (char *)workspace;
+    unsigned long long *keys = (unsigned long long *)(ws + L.off_wta);
+    HeadOut head;
+    head.part = (float4 *)(ws + align256(L.total));
+    head.slots = L.n_chunks * L.NU;
+    head.beta_log2e = beta * 1.4426950408889634f;
+    int rc;
+    if ((rc = launch_sliding_prep(p, L, cam, proj, ws, stream))) return rc;
+    // no hand-over to the tensor-core kernel here (it has no head epilogue): flagged tiles go to the per-cell fallback,
+    // which writes the same partials
+    const uint32_t thr = 0xffffffffu;
+    rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, nullptr, keys, thr, head, stream)
+       : p.k == 5 ? launch_k<5>(cfg, p, L, ws, nullptr, keys, thr, head, stream)
+                  : launch_k<7>(cfg, p, L, ws, nullptr, keys, thr, head, stream);
+    if (rc) return rc;
+    if ((rc = launch_fallback_forward(p, L, cam, proj, ws, nullptr, keys, head, thr, stream))) return rc;
+    head_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, head, soft_disparity, best, index,
+                                                                                 mask, head_state, threshold);
+    CUSTMA_LAUNCH_CHECK("head_decode_kernel");
     return CUSTMA_OK;
 }
 

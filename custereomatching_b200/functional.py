@@ -204,6 +204,65 @@ def wta_masked(camera, projector, D: int = 0, kernel_size: int = 5, threshold: f
     return best, index, mask, mdisp
 
 
+class _SoftDisparity(torch.autograd.Function):
+    """Fused head: masked soft-argmax disparity straight from the images; backward through the same kernels, no volume."""
+
+    @staticmethod
+    def forward(ctx, camera, projector, D, kernel_size, beta, threshold):
+        _check_input(camera, "camera")
+        _check_input(projector, "projector")
+        B, H, W, batched = _shape_bhw(camera, projector)
+        D, k = int(D), int(kernel_size)
+        lead = (B,) if batched else ()
+        with torch.cuda.device(camera.device):
+            dev = camera.device
+            soft = torch.empty(lead + (H, W), dtype=torch.float32, device=dev)
+            best = torch.empty(lead + (H, W), dtype=torch.float32, device=dev)
+            index = torch.empty(lead + (H, W), dtype=torch.int32, device=dev)
+            mask = torch.empty(lead + (H, W), dtype=torch.float32, device=dev)
+            state = torch.empty(lead + (H, W, 4), dtype=torch.float32, device=dev)
+            nbytes = binding.head_workspace_bytes(B, H, W, D, k, 0)
+            if nbytes == 0:
+                raise RuntimeError(f"the fused disparity head needs kernel_size 3 or 5 and valid sizes (got kernel_size={k}, "
+                                   f"shape {tuple(camera.shape)}, D={D})")
+            ws, ws_ptr = _workspace(nbytes, dev)
+            stream = torch.cuda.current_stream(dev)
+            binding.forward_head(camera.data_ptr(), projector.data_ptr(), soft.data_ptr(), best.data_ptr(), index.data_ptr(),
+                                 mask.data_ptr(), state.data_ptr(), beta, threshold, B, H, W, D, k, 0, ws_ptr, nbytes,
+                                 stream.cuda_stream)
+            ws.record_stream(stream)
+        ctx.save_for_backward(camera, projector, state)
+        ctx.cfg = (B, H, W, D, k, float(beta))
+        ctx.mark_non_differentiable(best, index, mask)
+        return soft, best, index, mask
+
+    @staticmethod
+    def backward(ctx, soft_grad, _gb, _gi, _gm):
+        camera, projector, state = ctx.saved_tensors
+        B, H, W, D, k, beta = ctx.cfg
+        soft_grad = soft_grad.contiguous()
+        if soft_grad.dtype != torch.float32:
+            raise RuntimeError(f"soft_disparity gradient must be float32, got {soft_grad.dtype}")
+        with torch.cuda.device(camera.device):
+            camera_grad = torch.empty_like(camera)
+            nbytes = binding.head_workspace_bytes(B, H, W, D, k, 0)
+            ws, ws_ptr = _workspace(nbytes, camera.device)
+            stream = torch.cuda.current_stream(camera.device)
+            binding.backward_head(soft_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(), state.data_ptr(), beta,
+                                  camera_grad.data_ptr(), B, H, W, D, k, 0, ws_ptr, nbytes, stream.cuda_stream)
+            ws.record_stream(stream)
+        return camera_grad, None, None, None, None, None
+
+
+def soft_disparity(camera, projector, D: int = 0, kernel_size: int = 5, beta: float = 50.0, threshold: float = 0.6):
+    """Fused differentiable disparity head: (soft_disparity * mask, best, index, mask), differentiable w.r.t. the camera.
+
+    soft_disparity = sum_s softmax_s(beta * cost)[s] * s (examples/verify.py:31-39 with softargmax_beta = 50 at :11; the
+    disparity of examples/test.py:85-86), mask = best > threshold (verify.py:72-74).  The cost volume is never written:
+    forward and backward recompute it tile by tile inside the kernels.  threshold < -1 gives the unmasked soft disparity."""
+    return _SoftDisparity.apply(camera, projector, D, kernel_size, beta, threshold)
+
+
 def ingest_u8(image_u8: torch.Tensor, channel: int = 0, scale: float = 1.0 / 255.0) -> torch.Tensor:
     """uint8 CUDA image [H,W], [H,W,Ch], [B,H,W,Ch] -> float32 plane(s) of one channel times scale
     (examples/verify.py:138-142,149: cv2.imread(...) / 255, then [:, :, 0])."""

@@ -118,6 +118,28 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
                          int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, int32_t row_begin,
                          int32_t row_end, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Fused differentiable disparity head: the caller on the output side of the path (examples/verify.py:31-39 soft_argmax
+ * with softargmax_beta = 50, :72-74 confidence mask; examples/test.py:79-86 disparity = column - correspondence, times the
+ * mask) computed WITHOUT materialising the cost volume:
+ *   w[s]           = softmax over the last axis of beta * cost (cells that do not exist take no part)
+ *   soft_disparity = mask * sum_s w[s] * s        [B,H,W] fp32 (banded: s is the disparity; full: column - projector column)
+ *   best, index    as custma_forward (may be NULL together);  mask [B,H,W] fp32 = best > mask_threshold (may be NULL;
+ *                  pass a threshold below -1 for an all-ones mask)
+ *   head_state     [B,H,W,4] fp32, 16-byte aligned: what custma_backward_head needs (may be NULL for inference)
+ * custma_backward_head turns d loss / d soft_disparity into the camera gradient: every cell's upstream gradient
+ * beta * w[s] * (s - soft) * mask * gd is rebuilt inside the backward kernel from head_state, so neither the volume nor a
+ * volume-sized gradient is ever written or read (0 bytes per cell of HBM traffic instead of 8).
+ * Sliding-window kernels only: kernel_size 3 or 5, no CUSTMA_FLAG_DIRECT / CUSTMA_FLAG_TENSOR; one workspace size
+ * (custma_head_workspace_bytes) serves both calls. */
+size_t custma_head_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags);
+int custma_forward_head(const float *camera, const float *projector, float *soft_disparity, float *best, int32_t *index,
+                        float *mask, float *head_state, float beta, float mask_threshold, int32_t B, int32_t H, int32_t W,
+                        int32_t D, int32_t kernel_size, uint32_t flags, void *workspace, size_t workspace_bytes,
+                        void *stream);
+int custma_backward_head(const float *soft_disparity_grad, const float *camera, const float *projector,
+                         const float *head_state, float beta, float *camera_grad, int32_t B, int32_t H, int32_t W, int32_t D,
+                         int32_t kernel_size, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
+
 /* 8-bit ingestion (examples/verify.py:138-142,149 load PNGs with cv2, divide by 255 and take channel 0):
  * dst[b,h,w] = src[b,h,w,channel] * scale for an interleaved uint8 image [B,H,W,channels] in device memory. */
 int custma_ingest_u8(const uint8_t *src, float *dst, int32_t B, int32_t H, int32_t W, int32_t channels, int32_t channel,

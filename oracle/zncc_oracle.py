@@ -199,6 +199,38 @@ def soft_argmax(vol: torch.Tensor, beta: float = SOFTARGMAX_BETA) -> torch.Tenso
     return (sm * idx).sum(-1)
 
 
+def soft_disparity_head(camera, projector, D: int, kernel_size: int, beta: float = SOFTARGMAX_BETA,
+                        threshold: float = MASK_THRESHOLD, soft_grad=None, dtype=torch.float64):
+    """The example-level disparity head on top of the volume (the oracle of custma_forward_head / custma_backward_head):
+    soft_argmax of examples/verify.py:31-39 on the last axis, disparity = column - correspondence and the product with the
+    confidence mask of examples/test.py:79-86 (mask = best > threshold, verify.py:72-74, detached as there).
+    D > 0: banded volume, the axis is the disparity itself and cells with w - s < 0 take no part; D == 0: the reference's
+    [H,W,W] volume, soft disparity = column - sum_d softmax * d.
+    Returns (soft * mask, best, mask, weights' mean absolute deviation of s, camera_grad or None); the camera gradient is
+    autograd's for the loss sum(soft * mask * soft_grad)."""
+    cam = _as_tensor(camera, dtype).clone().requires_grad_(soft_grad is not None)
+    proj = _as_tensor(projector, dtype)
+    H, W = cam.shape
+    if D > 0:
+        vol = cost_volume_banded(cam, proj, D, kernel_size, dtype=dtype, invalid=float("-inf"))
+        s = torch.arange(D, dtype=dtype)[None, None, :].expand(H, W, D)
+    else:
+        vol = cost_volume_full(cam, proj, kernel_size, dtype=dtype)
+        s = torch.arange(W, dtype=dtype)[None, :, None] - torch.arange(W, dtype=dtype)[None, None, :]
+        s = s.expand(H, W, W)
+    w = torch.softmax(vol * beta, dim=-1)                          # verify.py:34 (exp(-inf) = 0 for missing cells)
+    soft = (w * s).sum(-1)                                         # verify.py:36-38 / test.py:85
+    best = vol.detach().max(dim=-1).values
+    mask = (best > threshold).to(dtype)                            # verify.py:74
+    out = soft * mask                                              # test.py:86
+    mad = (w.detach() * (s - soft.detach()[..., None]).abs()).sum(-1)
+    grad = None
+    if soft_grad is not None:
+        (out * _as_tensor(soft_grad, dtype)).sum().backward()
+        grad = cam.grad.detach()
+    return out.detach(), best, mask, mad, grad
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Timed CPU baseline (north_star: "a pure-PyTorch CPU reimplementation ... timed on the box's own host cores")
 # ----------------------------------------------------------------------------------------------------------------

@@ -772,3 +772,118 @@ def test_misaligned_gradient_view_is_copied_not_faulted():
         binding.backward(gview.data_ptr(), dev(cam).data_ptr(), dev(proj).data_ptr(), out.data_ptr(), 1, H, W, D, k, 0,
                          ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused differentiable disparity head: soft-argmax (examples/verify.py:31-39, beta = 50) times the
+# confidence mask (:72-74), forward and backward without a volume
+# ---------------------------------------------------------------------------------------------------------------
+HEAD_BETA = 50.0
+# The head amplifies cost differences by beta: a cost error dc moves a softmax weight by beta*dc (relative) and the soft
+# disparity by at most beta * dc * MAD, MAD = the weights' mean absolute deviation of s (first-order perturbation of
+# sum_s w_s s).  With the cost tolerance 1e-5 that is 5e-4 * MAD pixels; 1e-4 px of slack for the exp2 approximation.
+def assert_soft_close(soft, ref, mad, what="soft disparity"):
+    err = np.abs(np.asarray(soft, np.float64) - ref)
+    bound = HEAD_BETA * COST_TOL * mad + 1e-4
+    bad = err > bound
+    assert not bad.any(), f"{what}: {bad.sum()} pixels out of bound, worst {err[bad].max():.3e} (bound {bound[bad].min():.3e})"
+
+
+HEAD_CASES = [  # H, W, D, k
+    (24, 90, 48, 5), (31, 260, 192, 5), (17, 77, 20, 3), (12, 50, 0, 5), (40, 300, 100, 5), (9, 140, 256, 5),
+]
+
+
+def _matched_pair(H, W, seed, s_true=9, noise=0.02):
+    rng = np.random.RandomState(seed)
+    proj = rng.rand(H, W).astype(np.float32)
+    cam = rng.rand(H, W).astype(np.float32)
+    cam[:, W // 3:] = proj[:, W // 3 - s_true:W - s_true] + noise * rng.randn(H, W - W // 3).astype(np.float32)
+    return cam.astype(np.float32), proj
+
+
+@pytest.mark.parametrize("H,W,D,k", HEAD_CASES)
+def test_fused_head_forward_backward_vs_oracle(H, W, D, k):
+    cam, proj = _matched_pair(H, W, seed=H * 100 + W)
+    gd = np.random.RandomState(3).randn(H, W).astype(np.float32)
+    ref_soft, ref_best, ref_mask, mad, ref_grad = zo.soft_disparity_head(cam, proj, D, k, HEAD_BETA, 0.6, soft_grad=gd)
+    camt = dev(cam).requires_grad_(True)
+    soft, best, index, mask = cb.soft_disparity(camt, dev(proj), D, k, beta=HEAD_BETA, threshold=0.6)
+    b2, i2, m2, _ = cb.wta_masked(dev(cam), dev(proj), D, k, threshold=0.6)
+    assert torch.equal(best, b2) and torch.equal(index, i2) and torch.equal(mask, m2)       # same WTA as the plain path
+    near = np.abs(ref_best.numpy() - 0.6) <= COST_TOL
+    assert np.array_equal(mask.cpu().numpy()[~near], ref_mask.numpy()[~near])
+    ok = ~near
+    assert_soft_close(soft.detach().cpu().numpy()[ok], ref_soft.numpy()[ok], mad.numpy()[ok])
+    assert 0.2 < mask.mean().item() < 0.95
+    soft.backward(dev(gd))
+    # gradient: the same beta amplification (weights to ~beta * 1e-6 relative in fp32) -> 1e-4 of the gradient scale
+    g = camt.grad.cpu().numpy()
+    scale = np.abs(ref_grad.numpy()).max()
+    assert np.isfinite(g).all()
+    assert np.abs(g - ref_grad.numpy()).max() <= 1e-4 * scale, np.abs(g - ref_grad.numpy()).max() / scale
+
+
+def test_fused_head_equals_unfused_gpu_path():
+    """Fusion check in fp32 on the device: soft-argmax + mask in torch on the materialised volume, autograd through
+    custma's own backward, against the fused head (which never writes the volume)."""
+    H, W, D, k = 60, 420, 192, 5
+    cam, proj = _matched_pair(H, W, seed=5, s_true=23)
+    gd = torch.randn(H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    c1 = dev(cam).requires_grad_(True)
+    vol = cb.cost_volume(c1, dev(proj), D, k)
+    valid = (torch.arange(W, device="cuda")[:, None] - torch.arange(D, device="cuda")[None, :]) >= 0
+    logits = torch.where(valid[None], vol * HEAD_BETA, torch.full_like(vol, float("-inf")))
+    w = torch.softmax(logits, dim=-1)
+    soft_ref = (w * torch.arange(D, device="cuda", dtype=torch.float32)).sum(-1)
+    best_ref = torch.where(valid[None], vol, torch.full_like(vol, float("-inf"))).max(dim=-1).values.detach()
+    mask_ref = (best_ref > 0.6).float()
+    (soft_ref * mask_ref * gd).sum().backward()
+    c2 = dev(cam).requires_grad_(True)
+    soft, best, index, mask = cb.soft_disparity(c2, dev(proj), D, k, beta=HEAD_BETA, threshold=0.6)
+    assert torch.equal(mask, mask_ref) and torch.equal(best, best_ref)
+    assert float((soft - soft_ref * mask_ref).abs().max()) <= 2e-3
+    soft.backward(gd)
+    scale = float(c1.grad.abs().max())
+    assert float((c2.grad - c1.grad).abs().max()) <= 1e-4 * scale
+    # deterministic, and batched == per pair
+    c3 = dev(cam).requires_grad_(True)
+    s3, *_ = cb.soft_disparity(c3, dev(proj), D, k, beta=HEAD_BETA, threshold=0.6)
+    s3.backward(gd)
+    assert torch.equal(s3, soft) and torch.equal(c3.grad, c2.grad)
+    cb2 = torch.stack([dev(cam), dev(cam).flip(0)]).contiguous().requires_grad_(True)
+    pb2 = torch.stack([dev(proj), dev(proj).flip(0)]).contiguous()
+    sb, *_ = cb.soft_disparity(cb2, pb2, D, k, beta=HEAD_BETA, threshold=0.6)
+    sb.backward(torch.stack([gd, gd.flip(0)]))
+    assert torch.equal(sb[0], soft) and torch.equal(cb2.grad[0], c2.grad)
+
+
+def test_fused_head_on_low_texture_input_uses_the_fallback_partials():
+    """A smooth scene flags every tile of the sliding-window path: the head's partials then come from the per-cell
+    fallback kernels (no tensor-core hand-over in head mode) and must still match the oracle."""
+    H, W, D, k = 24, 200, 64, 5
+    rng = np.random.RandomState(8)
+    xx = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)
+    yy = np.arange(H, dtype=np.float32)[:, None].repeat(W, 1)
+    scene = lambda sh: 0.5 + 0.4 * np.sin((xx + sh) * 0.05) * np.cos(yy * 0.1)
+    cam = np.ascontiguousarray(scene(0) + 0.01 * (rng.rand(H, W) - 0.5), np.float32)
+    proj = np.ascontiguousarray(scene(12) + 0.01 * (rng.rand(H, W) - 0.5), np.float32)
+    gd = rng.randn(H, W).astype(np.float32)
+    ref_soft, ref_best, ref_mask, mad, ref_grad = zo.soft_disparity_head(cam, proj, D, k, HEAD_BETA, -2.0, soft_grad=gd)
+    camt = dev(cam).requires_grad_(True)
+    soft, best, index, mask = cb.soft_disparity(camt, dev(proj), D, k, beta=HEAD_BETA, threshold=-2.0)
+    assert mask.min().item() == 1.0
+    assert_cost_close(best.cpu().numpy(), ref_best.numpy(), what="best")
+    assert_soft_close(soft.detach().cpu().numpy(), ref_soft.numpy(), mad.numpy())
+    soft.backward(dev(gd))
+    truth = ref_grad.numpy()
+    # low-texture: the fp32 reference arithmetic itself is ~1e-4 of scale from fp64 here (tiny denominators, times beta)
+    assert np.abs(camt.grad.cpu().numpy() - truth).max() <= 5e-4 * np.abs(truth).max()
+
+
+def test_fused_head_refuses_what_it_cannot_do():
+    cam, proj = rand_pair(16, 40, seed=1)
+    with pytest.raises(RuntimeError):
+        cb.soft_disparity(dev(cam), dev(proj), 16, 7)            # no backward fast path for k = 7
+    with pytest.raises(RuntimeError):
+        cb.soft_disparity(dev(cam), dev(proj), 16, 5, beta=-1.0)
