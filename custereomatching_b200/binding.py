@@ -39,6 +39,8 @@ SYMBOLS = (
     "custma_backward",
     "custma_backward_rows",
     "custma_ingest_u8",
+    "custma_backward_projector_workspace_bytes",
+    "custma_backward_projector",
     "custma_head_workspace_bytes",
     "custma_forward_head",
     "custma_backward_head",
@@ -64,7 +66,8 @@ def _declare(lib):
     lib.custma_last_error.argtypes = []
     lib.custma_launch_count.restype = ctypes.c_uint64
     lib.custma_launch_count.argtypes = []
-    for name in ("custma_forward_workspace_bytes", "custma_backward_workspace_bytes", "custma_head_workspace_bytes"):
+    for name in ("custma_forward_workspace_bytes", "custma_backward_workspace_bytes", "custma_head_workspace_bytes",
+                 "custma_backward_projector_workspace_bytes"):
         fn = getattr(lib, name)
         fn.restype = _size
         fn.argtypes = [_i32, _i32, _i32, _i32, _i32, _u32]
@@ -83,6 +86,8 @@ def _declare(lib):
     lib.custma_backward_rows.restype = ctypes.c_int
     lib.custma_backward_rows.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32, _ptr,
                                          _size, _ptr]
+    lib.custma_backward_projector.restype = ctypes.c_int
+    lib.custma_backward_projector.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_forward_head.restype = ctypes.c_int
     lib.custma_forward_head.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_float, ctypes.c_float, _i32, _i32,
                                         _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
@@ -176,6 +181,16 @@ def backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W,
     rc = load().custma_backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin,
                                      row_end, flags, ws_ptr or None, ws_bytes, stream or None)
     check(rc, "custma_backward_rows")
+
+
+def backward_projector_workspace_bytes(B, H, W, D, k, flags=0) -> int:
+    return int(load().custma_backward_projector_workspace_bytes(B, H, W, D, k, flags))
+
+
+def backward_projector(grad_ptr, camera_ptr, projector_ptr, projector_grad_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    rc = load().custma_backward_projector(grad_ptr, camera_ptr, projector_ptr, projector_grad_ptr, B, H, W, D, k, flags,
+                                          ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_backward_projector")
 
 
 def head_workspace_bytes(B, H, W, D, k, flags=0) -> int:

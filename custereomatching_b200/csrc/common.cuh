@@ -90,6 +90,11 @@ int launch_direct_backward(const Problem &p, const float *grad, const float *cam
                            const float *cmean, const float *cex2, const float *pmean, const float *pey2,
                            float *patch_grad /* [B,H,W,k*k] workspace */, float *camera_grad, cudaStream_t stream);
 
+int launch_direct_backward_projector(const Problem &p, const float *grad, const float *cam, const float *proj,
+                                     const float *cmean, const float *cex2, const float *pmean, const float *pey2,
+                                     float *patch_grad /* [B,H,W,k*k] workspace */, float *projector_grad,
+                                     cudaStream_t stream);
+
 // sliding-window kernels (sliding_forward.cu / sliding_backward.cu); return CUSTMA_ERR_UNSUPPORTED if the
 // (k, mode) combination has no instantiation, in which case the caller falls back to the direct kernels.
 bool sliding_forward_supported(const Problem &p);

@@ -234,6 +234,36 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
                          workspace, workspace_bytes, stream_);
 }
 
+// ---- gradient with respect to the projector image (the reference returns None for it) -----------
+size_t custma_backward_projector_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    Problem p;
+    if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
+    (void)flags;
+    return stats_bytes(p) + align256((size_t)p.pixels() * p.k * p.k * sizeof(float));
+}
+
+int custma_backward_projector(const float *cost_volume_grad, const float *camera, const float *projector,
+                              float *projector_grad, int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags,
+                              void *workspace, size_t workspace_bytes, void *stream_) {
+    Problem p;
+    int rc = make_problem(B, H, W, D, k, &p);
+    if (rc) return rc;
+    if (!cost_volume_grad || !camera || !projector || !projector_grad)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "cost_volume_grad, camera, projector and projector_grad must not be NULL");
+    if (flags & CUSTMA_FLAG_TENSOR) return set_error(CUSTMA_ERR_UNSUPPORTED, "no tensor-core kernel for the projector gradient");
+    if ((rc = check_image_alignment(cost_volume_grad, "cost_volume_grad")) || (rc = check_image_alignment(camera, "camera")) ||
+        (rc = check_image_alignment(projector, "projector")) || (rc = check_image_alignment(projector_grad, "projector_grad")))
+        return rc;
+    if ((rc = check_device())) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    StatsPtrs s;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, custma_backward_projector_workspace_bytes(B, H, W, D, k, flags), &s))) return rc;
+    if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
+    if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+    return launch_direct_backward_projector(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,
+                                            (float *)s.rest, projector_grad, stream);
+}
+
 // ---- fused differentiable disparity head -------------------------------------------------------
 size_t custma_head_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
     Problem p;

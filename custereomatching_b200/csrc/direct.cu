@@ -128,6 +128,12 @@ int launch_direct_forward(const Problem &p, const float *cam, const float *proj,
 // Dynamic shared memory per warp: k*k (centred camera patch) + 2*C (a_d and pm_d of this pixel).
 constexpr int kBwdWarps = 4;
 
+// SWAP = false: gradient with respect to the camera image (what the reference computes).  SWAP = true: with respect to
+// the PROJECTOR image - ZNCC is symmetric in its two patches, so the same kernel runs with the roles exchanged: the
+// pixel is a projector pixel (h, d), the loop runs over the camera columns w that meet it (banded: w = d + s), `cam` /
+// `cmean` / `cex2` are the projector's arrays and vice versa.  The reference has no such kernel
+// (custma/stereo_matching_wrapper.py:33 returns None for the projector): SURVEY.md 8f #2.
+template <bool SWAP>
 __global__ void __launch_bounds__(kBwdWarps * 32)
     direct_patch_grad_kernel(Problem p, const float *__restrict__ grad, const float *__restrict__ cam,
                              const float *__restrict__ proj, const float *__restrict__ cmean,
@@ -138,9 +144,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     const int64_t pix = (int64_t)blockIdx.x * kBwdWarps + warp;
     if (pix >= p.pixels()) return;
     const int kk = p.k * p.k;
-    const int w = (int)(pix % p.W);
+    const int w = (int)(pix % p.W);     // SWAP: the projector column d of this pixel
     const int h = (int)((pix / p.W) % p.H);
-    const int64_t plane_off = (pix / ((int64_t)p.H * p.W)) * (int64_t)p.H * p.W;
+    const int64_t bb = pix / ((int64_t)p.H * p.W);
+    const int64_t plane_off = bb * (int64_t)p.H * p.W;
     const float *cam_plane = cam + plane_off, *proj_plane = proj + plane_off;
     const float *pm_row = pmean + plane_off + (int64_t)h * p.W, *ey2_row = pey2 + plane_off + (int64_t)h * p.W;
     float *camc = smem + (size_t)warp * (kk + 2 * p.C);
@@ -150,18 +157,22 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
     for (int t = lane; t < kk; t += 32)
         camc[t] = query_ij(cam_plane, p.H, p.W, h + t / p.k - p.r, w + t % p.k - p.r) - cm;
     __syncwarp();
+    const bool grow = h >= p.g0 && h < p.g1;
+    const int64_t grow_base = (bb * p.grows() + (h - p.g0)) * p.W;
 
     float bsum = 0.f;
     for (int c = lane; c < p.C; c += 32) {
-        const int d = p.banded ? w - c : c;
+        // the other image's column this cell pairs the pixel with
+        const int d = SWAP ? (p.banded ? w + c : c) : (p.banded ? w - c : c);
         float a = 0.f, pm = 0.f;
-        if (d >= 0) {
+        if (d >= 0 && d < p.W) {
             pm = pm_row[d];
             const float ey2 = ey2_row[d];
             const float exy = cell_exy(camc, proj_plane, p.H, p.W, p.k, p.r, h, d, pm);
             const float den = sqrtf(fmaf(ex2, ey2, kEps));
-            const int64_t bb = pix / ((int64_t)p.H * p.W);
-            const float g = (h >= p.g0 && h < p.g1) ? grad[((bb * p.grows() + (h - p.g0)) * p.W + w) * p.C + c] : 0.f;
+            // cell [h, camera column, last-axis index]: camera column = w (or d when swapped); banded index c, full index = projector column
+            const int64_t gi = SWAP ? (grow_base + d) * p.C + (p.banded ? c : w) : (grow_base + w) * p.C + c;
+            const float g = grow ? grad[gi] : 0.f;
             a = g / den;
             bsum += g * ey2 * (exy + kEps) / (den * den * den);
         }
@@ -177,9 +188,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32)
         if (y >= 0 && y < p.H) {
             const float *prow = proj_plane + (int64_t)y * p.W;
             for (int c = lane; c < p.C; c += 32) {
-                const int d = p.banded ? w - c : c;
+                const int d = SWAP ? (p.banded ? w + c : c) : (p.banded ? w - c : c);
                 const int x = d + xo;
-                if (d >= 0) acc = fmaf(a_s[c], ((x >= 0 && x < p.W) ? __ldg(prow + x) : 0.f) - pm_s[c], acc);
+                if (d >= 0 && d < p.W) acc = fmaf(a_s[c], ((x >= 0 && x < p.W) ? __ldg(prow + x) : 0.f) - pm_s[c], acc);
             }
         } else {
             for (int c = lane; c < p.C; c += 32) acc = fmaf(a_s[c], -pm_s[c], acc);  // zero-padded row: proj = 0
@@ -213,23 +224,35 @@ __global__ void __launch_bounds__(256)
     camera_grad[pix] = acc;
 }
 
-int launch_direct_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
-                           const float *cmean, const float *cex2, const float *pmean, const float *pey2,
-                           float *patch_grad, float *camera_grad, cudaStream_t stream) {
+static int launch_direct_backward_impl(const Problem &p, bool swap, const float *grad, const float *cam, const float *proj,
+                                       const float *cmean, const float *cex2, const float *pmean, const float *pey2,
+                                       float *patch_grad, float *image_grad, cudaStream_t stream) {
     const size_t smem = (size_t)kBwdWarps * (p.k * p.k + 2 * p.C) * sizeof(float);
     if (smem > 200 * 1024)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "direct backward: last axis %d too long for shared memory", p.C);
+    auto kern = swap ? direct_patch_grad_kernel<true> : direct_patch_grad_kernel<false>;
     if (smem > 48 * 1024)
-        CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(direct_patch_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)smem));
+        CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (p.pixels() + kBwdWarps - 1) / kBwdWarps;
-    direct_patch_grad_kernel<<<(unsigned)blocks, kBwdWarps * 32, smem, stream>>>(p, grad, cam, proj, cmean, cex2,
-                                                                                pmean, pey2, patch_grad);
+    kern<<<(unsigned)blocks, kBwdWarps * 32, smem, stream>>>(p, grad, cam, proj, cmean, cex2, pmean, pey2, patch_grad);
     CUSTMA_LAUNCH_CHECK("direct_patch_grad_kernel");
     const int64_t gblocks = (p.pixels() + 255) / 256;
-    gather_patch_grad_kernel<<<(unsigned)gblocks, 256, 0, stream>>>(p, patch_grad, camera_grad);
+    gather_patch_grad_kernel<<<(unsigned)gblocks, 256, 0, stream>>>(p, patch_grad, image_grad);
     CUSTMA_LAUNCH_CHECK("gather_patch_grad_kernel");
     return CUSTMA_OK;
+}
+
+int launch_direct_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
+                           const float *cmean, const float *cex2, const float *pmean, const float *pey2,
+                           float *patch_grad, float *camera_grad, cudaStream_t stream) {
+    return launch_direct_backward_impl(p, false, grad, cam, proj, cmean, cex2, pmean, pey2, patch_grad, camera_grad, stream);
+}
+
+// gradient with respect to the projector image: the same two kernels with the two images' roles exchanged
+int launch_direct_backward_projector(const Problem &p, const float *grad, const float *cam, const float *proj,
+                                     const float *cmean, const float *cex2, const float *pmean, const float *pey2,
+                                     float *patch_grad, float *projector_grad, cudaStream_t stream) {
+    return launch_direct_backward_impl(p, true, grad, proj, cam, pmean, pey2, cmean, cex2, patch_grad, projector_grad, stream);
 }
 
 }  // namespace custma

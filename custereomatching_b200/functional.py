@@ -157,8 +157,35 @@ def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: to
     return camera_grad
 
 
+def backward_projector(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: torch.Tensor, kernel_size: int,
+                       D: int = 0, *, flags: int = 0) -> torch.Tensor:
+    """Gradient of sum(cost * cost_volume_grad) with respect to the PROJECTOR image (the reference has none:
+    custma/stereo_matching_wrapper.py:33 returns None); same leading shape as projector."""
+    _check_input(cost_volume_grad, "cost_volume_grad")
+    _check_input(camera, "camera")
+    _check_input(projector, "projector")
+    B, H, W, batched = _shape_bhw(camera, projector)
+    D, k = int(D), int(kernel_size)
+    C = D if D > 0 else W
+    lead = (B,) if batched else ()
+    if tuple(cost_volume_grad.shape) != lead + (H, W, C):
+        raise RuntimeError(f"cost_volume_grad must have shape {lead + (H, W, C)}, got {tuple(cost_volume_grad.shape)}")
+    with torch.cuda.device(camera.device):
+        projector_grad = torch.empty_like(projector)
+        nbytes = binding.backward_projector_workspace_bytes(B, H, W, D, k, flags)
+        if nbytes == 0:
+            binding.check(binding.ERR_INVALID_ARGUMENT, "custma_backward_projector_workspace_bytes")
+        ws, ws_ptr = _workspace(nbytes, camera.device)
+        stream = torch.cuda.current_stream(camera.device)
+        binding.backward_projector(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
+                                   projector_grad.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes, stream.cuda_stream)
+        ws.record_stream(stream)
+    return projector_grad
+
+
 class _CostVolume(torch.autograd.Function):
-    """Differentiable cost volume, banded or full, batched or not; gradient w.r.t. the camera image only."""
+    """Differentiable cost volume, banded or full, batched or not.  The camera always gets its gradient (as in the
+    reference); the projector gets one too when it requires it (an extension: the reference returns None for it)."""
 
     @staticmethod
     def forward(ctx, camera, projector, D, kernel_size, flags):
@@ -170,8 +197,12 @@ class _CostVolume(torch.autograd.Function):
     @staticmethod
     def backward(ctx, cost_volume_grad):
         camera, projector = ctx.saved_tensors
-        g = backward(cost_volume_grad.contiguous(), camera, projector, ctx.kernel_size, ctx.D, flags=ctx.flags)
-        return g, None, None, None, None
+        cost_volume_grad = cost_volume_grad.contiguous()
+        g = backward(cost_volume_grad, camera, projector, ctx.kernel_size, ctx.D, flags=ctx.flags) \
+            if ctx.needs_input_grad[0] else None
+        gp = backward_projector(cost_volume_grad, camera, projector, ctx.kernel_size, ctx.D) \
+            if ctx.needs_input_grad[1] else None
+        return g, gp, None, None, None
 
 
 def cost_volume(camera, projector, D: int = 0, kernel_size: int = 5, flags: int = 0) -> torch.Tensor:

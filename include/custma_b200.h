@@ -118,6 +118,16 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
                          int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, int32_t row_begin,
                          int32_t row_end, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Gradient of sum(cost_volume * cost_volume_grad) with respect to the PROJECTOR image.  The reference has none
+ * (custma/stereo_matching_wrapper.py:33 returns None); ZNCC is symmetric in its two patches, so this is the camera
+ * gradient's arithmetic (custma/src/stereo_matching_kernel.cu:75-179) with the two images' roles exchanged.  Runs on the
+ * direct two-pass kernels for every kernel_size (no sliding-window variant yet); deterministic, no atomics. */
+size_t custma_backward_projector_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size,
+                                                 uint32_t flags);
+int custma_backward_projector(const float *cost_volume_grad, const float *camera, const float *projector,
+                              float *projector_grad, int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size,
+                              uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Fused differentiable disparity head: the caller on the output side of the path (examples/verify.py:31-39 soft_argmax
  * with softargmax_beta = 50, :72-74 confidence mask; examples/test.py:79-86 disparity = column - correspondence, times the
  * mask) computed WITHOUT materialising the cost volume:

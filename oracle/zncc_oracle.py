@@ -162,6 +162,22 @@ def camera_grad_banded_autograd(camera, projector, band_grad, D: int, kernel_siz
     return cam.grad.detach()
 
 
+def projector_grad_autograd(camera, projector, cost_volume_grad, D: int, kernel_size: int, dtype=torch.float64):
+    """Gradient of sum(cost * cost_volume_grad) with respect to the PROJECTOR image by autograd (the oracle of
+    custma_backward_projector; the reference itself returns None for it, custma/stereo_matching_wrapper.py:33).
+    D > 0: banded volume (invalid cells carry no gradient); D == 0: the [H,W,W] volume."""
+    proj = _as_tensor(projector, dtype).clone().requires_grad_(True)
+    g = _as_tensor(cost_volume_grad, dtype)
+    if D > 0:
+        vol = cost_volume_banded(camera, proj, D, kernel_size, dtype=dtype, invalid=0.0)
+        W = proj.shape[1]
+        valid = (torch.arange(W)[:, None] - torch.arange(D)[None, :]) >= 0
+        (vol * g * valid[None].to(dtype)).sum().backward()
+    else:
+        (cost_volume_full(camera, proj, kernel_size, dtype=dtype) * g).sum().backward()
+    return proj.grad.detach()
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Winner-take-all, confidence mask, soft-argmax (examples/verify.py:31-39, 72-74; examples/test.py:78-86)
 # ----------------------------------------------------------------------------------------------------------------

@@ -887,3 +887,46 @@ def test_fused_head_refuses_what_it_cannot_do():
         cb.soft_disparity(dev(cam), dev(proj), 16, 7)            # no backward fast path for k = 7
     with pytest.raises(RuntimeError):
         cb.soft_disparity(dev(cam), dev(proj), 16, 5, beta=-1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# projector gradient: the reference returns None for it (custma/stereo_matching_wrapper.py:33)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,D,k", [(14, 40, 16, 5), (9, 33, 0, 5), (12, 30, 8, 3), (10, 28, 12, 4), (8, 36, 0, 7),
+                                     (20, 64, 64, 5), (6, 25, 25, 15)])
+def test_projector_gradient_vs_oracle_autograd(H, W, D, k):
+    cam, proj = rand_pair(H, W, seed=H * 31 + W)
+    C = D if D > 0 else W
+    g = np.random.RandomState(4).randn(H, W, C).astype(np.float32)
+    ref = zo.projector_grad_autograd(cam, proj, g, D, k).numpy()
+    out = cb.backward_projector(dev(g), dev(cam), dev(proj), k, D)
+    assert out.shape == (H, W)
+    assert_grad_close(out.cpu().numpy(), ref)
+    again = cb.backward_projector(dev(g), dev(cam), dev(proj), k, D)
+    assert torch.equal(out, again)                                   # deterministic: no atomics
+    # symmetry that the kernel exploits: for the reference-shaped volume, the projector gradient is the camera gradient
+    # of the transposed problem
+    if D == 0:
+        gt = np.ascontiguousarray(g.transpose(0, 2, 1))
+        sym = cb.backward(dev(gt), dev(proj), dev(cam), k, 0, flags=cb.FLAG_DIRECT)
+        assert_grad_close(out.cpu().numpy(), sym.cpu().numpy(), 1e-6)
+
+
+def test_projector_gradient_through_autograd_and_batches():
+    B, H, W, D, k = 2, 16, 48, 24, 5
+    cam, proj = rand_pair(H, W, seed=9, B=B)
+    wgt = torch.from_numpy(np.random.RandomState(5).randn(B, H, W, D).astype(np.float32)).cuda()
+    c, p = dev(cam).requires_grad_(True), dev(proj).requires_grad_(True)
+    vol = cb.cost_volume(c, p, D, k)
+    valid = (torch.arange(W, device="cuda")[:, None] - torch.arange(D, device="cuda")[None, :]) >= 0
+    (vol * wgt * valid).sum().backward()
+    assert c.grad is not None and p.grad is not None
+    for b in range(B):
+        gm = (wgt[b] * valid).cpu().numpy()
+        assert_grad_close(p.grad[b].cpu().numpy(), zo.projector_grad_autograd(cam[b], proj[b], gm, D, k).numpy())
+        assert_grad_close(c.grad[b].cpu().numpy(), zo.camera_grad_banded_autograd(cam[b], proj[b], gm, D, k).numpy())
+    # the drop-in Function keeps the reference's contract: no projector gradient
+    c2, p2 = dev(cam[0]).requires_grad_(True), dev(proj[0]).requires_grad_(True)
+    cv = custma.stereo_matching(c2, p2, 0, k)
+    cv.backward(torch.ones_like(cv))
+    assert p2.grad is None
