@@ -57,6 +57,8 @@ __device__ __forceinline__ float exp2_fast(float x) {
 
 // thread-local error message storage (custma_api.cu)
 int set_error(int code, const char *fmt, ...);
+// multiprocessors of the current device (148 when there is none: host-only layout checks)
+int device_sm_count();
 // process-wide count of kernels this library has launched (custma_launch_count)
 void note_launch();
 

@@ -22,6 +22,19 @@ int set_error(int code, const char *fmt, ...) {
     return code;
 }
 
+// SMs of the current device (B200: 148).  The tilings are sized from it; without a device (host-only layout checks)
+// the B200 count is assumed.
+int device_sm_count() {
+    static thread_local int cached_dev = -2, cached_sms = 148;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    if (dev == cached_dev) return cached_sms;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); return 148; }
+    cached_dev = dev; cached_sms = sms;
+    return sms;
+}
+
 static int check_device() {
     static thread_local int checked_device = -1;
     int dev = 0;

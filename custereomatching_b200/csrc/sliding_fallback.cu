@@ -12,7 +12,7 @@ namespace custma {
 
 constexpr int kFbWarps = 8;
 constexpr int kFbRows = kFallbackRows;
-constexpr int kFbGrid = 148 * 8;   // CTAs looping over the work list (they return at once when it is empty)
+static int fb_grid() { return device_sm_count() * 8; }   // CTAs looping over the work list (they return at once when it is empty)
 
 // chunk of the sliding tiling that owns cell (w, c) of column tile w_base
 __device__ __forceinline__ int cell_chunk(const Problem &p, const SlidingLayout &L, int w_base, int w, int c) {
@@ -267,7 +267,7 @@ int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const floa
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback forward: last axis %d too long for shared memory", p.C);
     if (smem > 48 * 1024)
         CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(fallback_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fallback_forward_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
+    fallback_forward_kernel<<<fb_grid(), kFbWarps * 32, smem, stream>>>(
         p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost,
         keys, tc_threshold, head);
@@ -287,7 +287,7 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
                                            (int)std::max<size_t>(smem, 48 * 1024)));
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
-    fallback_patch_grad_kernel<<<kFbGrid, kFbWarps * 32, smem, stream>>>(
+    fallback_patch_grad_kernel<<<fb_grid(), kFbWarps * 32, smem, stream>>>(
         p, L, grad, hg, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
         (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2),
         patch_grad, tc_threshold);

@@ -53,7 +53,8 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
     // backward: 1).  Independent of B, so that a batch and its pairs one by one give the same bits.
     // RB + K - 1 row steps must be a whole number of pair-sum-ring periods (K - 2).
     const int64_t tiles = (int64_t)L->n_wtiles * L->n_chunks;
-    const int64_t want = backward ? 2 * 148 : 4 * 148;
+    const int64_t sms = device_sm_count();
+    const int64_t want = backward ? 2 * sms : 4 * sms;
     auto fit_up = [&](int rows) { while ((rows + cfg.K - 1) % (cfg.K - 2)) ++rows; return rows; };
     int RB = 16;
     for (int nbands = 1; nbands <= p.H; ++nbands) {

@@ -1,9 +1,10 @@
 // Tensor-core backward: the camera gradient of ill-conditioned inputs on tcgen05 (sm_100a), the counterpart of
 // tc_forward.cu.
 //
-// What it restates: backward_cost_volume_kernel (reference custma/src/stereo_matching_kernel.cu:101-160).  Per cell the
-// reference forms  A = g / den,  B = g * ey2 * (exy + eps) / den^3  (:135,145-148) and adds the patch gradient
-// A * pc[p][tap] - B * cc[x][tap] to the k x k camera pixels of the window with atomicAdd (:150-158).  Summed over the
+// What it restates: get_patches_grad_kernel + patches_grad_to_image_kernel (reference
+// custma/src/stereo_matching_kernel.cu:75-152, :155-179).  Per cell the reference forms  A = g / den,
+// B = g * ey2 * (exy + eps) / den^3  (:135,:145-148) and adds the patch gradient A * pc[p][tap] - B * cc[x][tap] to the
+// per-pixel patch buffer with atomicAdd (:149), which a second kernel scatters to the image (:178).  Summed over the
 // projector columns of one camera pixel that is again a dense contraction:
 //     MMA1   D1[128 x 128]  = CC * PC^T                                 exy, as in the forward (3xTF32, fp32 in TMEM)
 //     epi1   a = g * rsqrt(ex2 * ey2 + eps)  -> two tf32 halves written back into TMEM (tcgen05.st),
@@ -449,15 +450,16 @@ __global__ void __launch_bounds__(256)
 }
 
 
-// Rows per tile: the fewest rounds of tiles over the persistent CTAs (148 assumed: the workspace query must give the
-// same answer without a device), little per-tile start-up (ring fill, halo rows).
+// Rows per tile: the fewest rounds of tiles over the persistent CTAs (one per SM of the current device; the workspace
+// query and the launch see the same device), little per-tile start-up (ring fill, halo rows).
 static int pick_rows(const Problem &p) {
     const int64_t per_row = (int64_t)p.B * ((p.W + MT - 1) / MT);
     int best_rb = RBMAX;
     double best_cost = 1e30;
     for (int rb = RBMAX; rb >= 4; --rb) {
         const int64_t tiles = per_row * ((p.H + rb - 1) / rb);
-        const double c = (double)((tiles + 147) / 148) * (rb + 2.0);
+        const int64_t sms = device_sm_count();
+        const double c = (double)((tiles + sms - 1) / sms) * (rb + 2.0);
         if (c < best_cost) { best_cost = c; best_rb = rb; }
     }
     return best_rb;
