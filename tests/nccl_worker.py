@@ -44,7 +44,11 @@ def main():
     cost, best, disp = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True)
     grad = cb.backward(g, cam, proj, k, D)
     rb, rd, rg = sh.row_band_sharded_step(cam, proj, D, k, cost_volume_grad_fn=lambda c, band: g[band.h0:band.h1].contiguous())
-    assert torch.equal(rb, best) and torch.equal(rd, disp), "row-band WTA differs"
+    # a crop has its own row bands and pivots: costs agree to rounding (not bit for bit), disparities outside near-ties
+    assert float((rb - best).abs().max()) <= 2e-6, "row-band best differs"
+    top2 = torch.topk(cost, 2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-5
+    assert torch.equal(rd[clear], disp[clear]), "row-band disparity differs outside near-ties"
     err = float((rg - grad).abs().max() / grad.abs().max())
     assert err <= 1e-5, f"row-band gradient differs by {err:.2e} of scale"
     # every rank holds the same gathered bits
