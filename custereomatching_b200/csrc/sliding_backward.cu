@@ -19,8 +19,6 @@
 // to per-chunk images; sliding_backward_finalize_kernel gathers them.
 // The upstream gradient is prefetched with per-thread cp.async (each thread reads back only what it copied, so no
 // barrier is involved), up to three row steps ahead.
-#include <cstdlib>
-
 #include "sliding_common.cuh"
 
 namespace custma {
@@ -615,445 +613,10 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     }
 }
 
-// ================================================================================================================
-// Split variant of the row loop: two thread groups per tile, twice the warps per SM.
-//
-// The single-group kernel above keeps two 64-register rings per thread (window sums of the products, vertical sums of
-// a), needs 255 registers, and so runs 8 warps per SM; ncu shows its warps waiting on fixed-latency dependencies and
-// shared-memory loads most of the time (issue slots 59 % busy, ~2000 cycles of latency per row step for ~1250 issue
-// slots).  Here the step is cut where the data flow is narrowest:
-//   group A   (BoxRing)  window sums -> exy -> a = g / den, Bs, Am of the thread's 4 x 4 cells
-//   group B   (SumRing)  vertical sums of a -> horizontal prefix sums -> T1 partials -> cross-lane sums, and all the
-//                        copies: row slots, upstream gradient rows (for A), tile sums
-// A thread of A hands its 16 values of a to the thread of B with the same tile coordinates through a private 64-byte
-// slot in shared memory (two stages); its Bs / Am partials go straight into the unit's transpose scratch.  Each half
-// fits 128 registers, so 16 warps are resident.  Same arithmetic, same summation order, same bits as the kernel above.
-//
-// Barriers (all mbarriers, no __syncthreads in the loop):
-//   full[slot]        B's cp.async (row data of the step, and the gradient row issued earlier) have landed: A and B wait
-//   empty[slot]       every B warp is done with the step (which implies its A warp is too): B waits before refilling
-//   hfull[stage][w]   A warp w has handed over its step;  hempty[stage][w]  B warp w has consumed it
-// A gradient stage is free as soon as A's hand-over of the step that used it arrives, so B refills it right then:
-// the gradient runs kSplitGradStages steps ahead without a barrier of its own.
-constexpr int kSplitGradStages = 5;
-constexpr int kSplitHand = 2;
-constexpr int kSplitLookahead = 4;
-
-template <int K, int NU, int WG>
-struct SplitGeom {
-    using F = SlideGeom<K, NU, WG>;
-    using G = BwdGeom<K, NU, WG>;
-    static constexpr int NT = F::NCONS, TPR = (NT + 31) / 32 * 32, NCW = TPR / 32;
-    static constexpr int ROW_FLOATS = F::NS * G::SLOT;
-    static constexpr int GRAD_FLOATS = kSplitGradStages * 16 * NT;
-    static constexpr int HAND_FLOATS = kSplitHand * 16 * NT;
-    static constexpr int XPOSE_PAR = G::UNITS * G::XPOSE_UNIT;
-    static constexpr int SMEM_FLOATS = ROW_FLOATS + GRAD_FLOATS + HAND_FLOATS + 2 * XPOSE_PAR;
-    static constexpr size_t SMEM_BYTES = (size_t)SMEM_FLOATS * sizeof(float);
-    static_assert(SMEM_BYTES <= 227 * 1024, "split backward: shared memory");
-};
-
-struct SplitBars {
-    uint64_t *full, *empty, *hfull, *hempty;   // hfull / hempty: [kSplitHand][NCW]
-};
-
-// ---- group A: window sums, cell epilogue, hand-over ----------------------------------------------------------------
-template <int K, int NU, int WG, int MODE, int DIR, bool HG>
-__device__ __forceinline__ void split_role_a(const Problem &p, float *smem, const SplitBars &bars, int rt, int b, int h0,
-                                             int rows, int w_base, int s_base, int steps, const float *__restrict__ grad,
-                                             const HeadGrad &hg) {
-    using F = SlideGeom<K, NU, WG>;
-    using G = BwdGeom<K, NU, WG>;
-    using SG = SplitGeom<K, NU, WG>;
-    constexpr int CL = F::CL, PL = F::PL, NS = F::NS, PERIOD = F::PERIOD, NT = F::NCONS;
-    const int l16 = rt & 15, u = rt >> 4, su = u % NU, wg = u / NU, warp = rt >> 5;
-    const int w0 = w_base + 4 * wg, s0 = s_base + 64 * su + 4 * l16;
-    const int pidx = 4 * (wg - 16 * su - l16 + 16 * NU - 1);
-    const int C = p.C;
-    const float seed = kEps / (float)K;
-    const float *gsm = smem + SG::ROW_FLOATS + 4 * rt;                       // [stage][4][NT] float4, this thread's
-    float *hand = smem + SG::ROW_FLOATS + SG::GRAD_FLOATS + 4 * rt;          // [stage][4][NT] float4
-    float *xrow = smem + SG::ROW_FLOATS + SG::GRAD_FLOATS + SG::HAND_FLOATS + u * G::XPOSE_UNIT + l16 * G::XPOSE_STRIDE + 8;
-    const float *gsrc = HG ? reinterpret_cast<const float *>(hg.state) + (((int64_t)b * p.H + h0) * p.W + w0) * 4
-                           : grad + (((int64_t)b * p.grows() + (h0 - p.g0)) * p.W + w0) * C + (MODE == 2 ? 0 : s0);
-    const int g_lo = HG ? 0 : max(0, p.g0 - h0), g_hi = HG ? rows : min(rows, p.g1 - h0);
-    const int64_t g_row = HG ? (int64_t)p.W * 4 : (int64_t)p.W * C;
-    uint32_t cmask = 0;
-    if (MODE == 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (w0 + i < p.W && w0 + i - (s0 + j) >= 0) cmask |= 1u << (4 * i + j);
-    }
-    uint64_t *hfull = bars.hfull + warp, *hempty = bars.hempty + warp;      // + stage * NCW
-
-    BoxRing<K> ring;
-    ring.clear();
-    int gstage = 0;   // t % kSplitGradStages
-#pragma unroll 1
-    for (int t0 = 0; t0 < steps; t0 += PERIOD) {
-#pragma unroll
-        for (int q = 0; q < PERIOD; ++q) {
-            const int t = t0 + q;
-            const int slot = t & (NS - 1), hs = t & (kSplitHand - 1);
-            mbar_wait(&bars.full[slot], (t / NS) & 1);
-            const float *S = smem + slot * G::SLOT;
-            const int hr = t - (K - 1);
-            const bool has_cells = hr >= g_lo && hr < g_hi;
-            float c[CL], pj[PL];
-#pragma unroll
-            for (int v = 0; v < CL / 4; ++v)
-                *reinterpret_cast<float4 *>(&c[4 * v]) = *reinterpret_cast<const float4 *>(S + 4 * wg + 4 * v);
-#pragma unroll
-            for (int v = 0; v < PL / 4; ++v)
-                *reinterpret_cast<float4 *>(&pj[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJ + pidx + 4 * v);
-            float bx[4][4];
-            ring.template step<DIR>(q, c, pj, seed, bx);
-
-            float a[4][4], bsam[8];   // Bs[0..4), Am[0..4)
-            if (has_cells) {
-                float a4[4], e4[4], sp[8], ey[8], gg[4][4];
-                *reinterpret_cast<float4 *>(a4) = *reinterpret_cast<const float4 *>(S + G::OFF_A + 4 * wg);
-                *reinterpret_cast<float4 *>(e4) = *reinterpret_cast<const float4 *>(S + G::OFF_EX2 + 4 * wg);
-                *reinterpret_cast<float4 *>(&sp[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx);
-                *reinterpret_cast<float4 *>(&sp[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_SP + pidx + 4);
-                *reinterpret_cast<float4 *>(&ey[0]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx);
-                *reinterpret_cast<float4 *>(&ey[4]) = *reinterpret_cast<const float4 *>(S + G::OFF_EY2 + pidx + 4);
-                if (MODE != 2) {
-                    const float *gs = gsm + gstage * (16 * NT);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<float4 *>(gg[i]) = *reinterpret_cast<const float4 *>(gs + i * (4 * NT));
-                    if (MODE == 1 && !HG) {   // whatever the caller left in the invalid cells of the gradient must not leak
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (!((cmask >> (4 * i + j)) & 1u)) gg[i][j] = 0.f;
-                    }
-                } else if (HG) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (w0 + i < p.W) st = __ldg(reinterpret_cast<const float4 *>(gsrc + hr * g_row + (int64_t)i * 4));
-                        gg[i][0] = st.x; gg[i][1] = st.y; gg[i][2] = st.z; gg[i][3] = st.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int s = s0 + j, d = w0 + i - s;
-                            const bool valid = w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s < p.D);
-                            gg[i][j] = valid ? __ldg(gsrc + hr * g_row + (int64_t)i * C + (p.banded ? s : d)) : 0.f;
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float bs = 0.f, am = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int di = i - j + 3;
-                        const float e = fmaf(-a4[i], sp[di], bx[i][j]);              // exy + eps
-                        const float rs = rsqrt_fast(fmaf(e4[i], ey[di], kEps));      // 1 / den
-                        float g = gg[i][j];
-                        if (HG) {
-                            g = exp2_fast(fmaf(e * rs, hg.beta_log2e, -gg[i][0])) * fmaf((float)(s0 + j), gg[i][1], -gg[i][2]);
-                            bool valid = true;
-                            if (MODE == 1) valid = (cmask >> (4 * i + j)) & 1u;
-                            if (MODE == 2) {
-                                const int d = w0 + i - (s0 + j);
-                                valid = w0 + i < p.W && d >= 0 && d < p.W && (!p.banded || s0 + j < p.D);
-                            }
-                            g = valid ? g : 0.f;
-                        }
-                        const float av = g * rs;                                     // a  = g / den               (:135,:145)
-                        a[i][j] = av;                                                // bc = g*ey2*(exy+eps)/den^3 (:147)
-                        bs = j == 0 ? (av * e) * (ey[di] * (rs * rs)) : fmaf(av * e, ey[di] * (rs * rs), bs);
-                        am = j == 0 ? av * sp[di] : fmaf(av, sp[di], am);
-                    }
-                    bsam[i] = bs;
-                    bsam[4 + i] = am;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bsam[i] = 0.f;
-            }
-            // ---- hand over: B's stage must be consumed (two steps ago), then a -> the private slot, Bs / Am -> this
-            // lane's row of the unit's transpose scratch (columns 8..15; B adds its T1 partials in columns 0..7)
-            if (t >= kSplitHand) mbar_wait(&hempty[hs * SG::NCW], ((t / kSplitHand) - 1) & 1);
-            if (has_cells) {
-                float *hd = hand + hs * (16 * NT);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4 *>(hd + i * (4 * NT)) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
-            }
-            {
-                float *xr = xrow + (t & 1) * SG::XPOSE_PAR;
-                *reinterpret_cast<float4 *>(xr) = make_float4(bsam[0], bsam[1], bsam[2], bsam[3]);
-                *reinterpret_cast<float4 *>(xr + 4) = make_float4(bsam[4], bsam[5], bsam[6], bsam[7]);
-            }
-            __syncwarp();
-            if ((rt & 31) == 0) mbar_arrive(&hfull[hs * SG::NCW]);
-            gstage = gstage + 1 == kSplitGradStages ? 0 : gstage + 1;
-        }
-    }
-}
-
-// ---- group B: copies, vertical sums of a, T1 partials, cross-lane and tile sums ------------------------------------
-template <int K, int NU, int WG, int MODE, bool HG>
-__device__ __forceinline__ void split_role_b(const Problem &p, const SlidingLayout &L, float *smem, const SplitBars &bars,
-                                             BwdRowLoader<K, NU, WG> &loader, int rt, int b, int h0, int rows, int w_base,
-                                             int s_base, int steps, const float *__restrict__ grad, const HeadGrad &hg,
-                                             float *__restrict__ T1tile, int T1pitch, float *__restrict__ AmRow,
-                                             float *__restrict__ BsRow) {
-    using F = SlideGeom<K, NU, WG>;
-    using G = BwdGeom<K, NU, WG>;
-    using SG = SplitGeom<K, NU, WG>;
-    constexpr int PL = F::PL, NS = F::NS, PERIOD = F::PERIOD, NT = F::NCONS;
-    constexpr int LA = kSplitLookahead, GS = kSplitGradStages;
-    const int l16 = rt & 15, u = rt >> 4, su = u % NU, wg = u / NU, warp = rt >> 5;
-    const int w0 = w_base + 4 * wg, s0 = s_base + 64 * su + 4 * l16;
-    const int pidx = 4 * (wg - 16 * su - l16 + 16 * NU - 1);
-    const int C = p.C;
-    const float inv_n = 1.f / (float)(K * K);
-    float *gsm = smem + SG::ROW_FLOATS + 4 * rt;
-    const float *hand = smem + SG::ROW_FLOATS + SG::GRAD_FLOATS + 4 * rt;
-    float *xps = smem + SG::ROW_FLOATS + SG::GRAD_FLOATS + SG::HAND_FLOATS + u * G::XPOSE_UNIT;
-    const float *gsrc = HG ? reinterpret_cast<const float *>(hg.state) + (((int64_t)b * p.H + h0) * p.W + w0) * 4
-                           : grad + (((int64_t)b * p.grows() + (h0 - p.g0)) * p.W + w0) * C + s0;
-    const int g_lo = HG ? 0 : max(0, p.g0 - h0), g_hi = HG ? rows : min(rows, p.g1 - h0);
-    const int64_t g_row = HG ? (int64_t)p.W * 4 : (int64_t)p.W * C, g_col = HG ? 4 : C;
-    uint64_t *hfull = bars.hfull + warp, *hempty = bars.hempty + warp;
-
-    // the gradient row (or, for the fused head, the per-pixel state) that step tg consumes -> its stage
-    auto issue_grad = [&](int tg, int stage) {
-        if (MODE == 2) return;   // scalar bodies read their gradient directly
-        const int hp = tg - (K - 1);
-        if (hp >= g_lo && hp < g_hi) {
-            float *gdst = gsm + stage * (16 * NT);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (MODE == 0 || w0 + i < p.W)   // columns past the image are never read as valid cells
-                    cp_async16(gdst + i * (4 * NT), gsrc + hp * g_row + (int64_t)i * g_col);
-        }
-    };
-    auto issue_rows = [&](int tl) {
-        const int sl = tl & (NS - 1);
-        float *Sl = smem + sl * G::SLOT;
-#pragma unroll
-        for (int n = 0; n < G::NCH; ++n) {
-            if (loader.dst[n] >= 0 && tl >= loader.first[n] && tl < loader.last[n]) cp_async16(Sl + loader.dst[n], loader.src[n]);
-            loader.src[n] += loader.stride[n];
-        }
-        cp_async_mbar_arrive(&bars.full[sl]);
-    };
-    // fixed-order sum of the per-unit partials of step ts -> workspace (as in the single-group kernel)
-    auto reduce_step = [&](int ts) {
-        if (ts < K - 1) return;
-        const int ty = ts - (K - 1);
-        const float *stg = smem + (ts & (NS - 1)) * G::SLOT + G::OFF_STG;
-        if (rt < G::TW) {
-            if (ty < L.RBH) {
-                const int x = rt;
-                float acc = 0.f;
-#pragma unroll
-                for (int g = 0; g < WG; ++g) {
-                    const int xi = x - 4 * g;
-                    if (xi >= 0 && xi < K + 3) {
-#pragma unroll
-                        for (int q = 0; q < NU; ++q) acc += stg[(g * NU + q) * 16 + xi];
-                    }
-                }
-                T1tile[(int64_t)ty * T1pitch + x] = acc;
-            }
-        } else if (rt >= 96 && rt < 96 + 2 * F::WTC) {
-            if (ty < rows) {
-                const int idx = rt - 96, w = idx % F::WTC, which = idx / F::WTC;  // 0: Bs, 1: Am
-                float acc = 0.f;
-#pragma unroll
-                for (int q = 0; q < NU; ++q) acc += stg[((w >> 2) * NU + q) * 16 + 8 + 4 * which + (w & 3)];
-                (which ? AmRow : BsRow)[(int64_t)ty * L.cs_pitch + w] = which ? acc * inv_n : acc;
-            }
-        }
-    };
-
-    // prologue: the gradient rows of the first GS steps, then the row data of the first LA steps (a slot's arrival also
-    // covers the gradient row issued before it)
-    for (int tg = 0; tg < GS && tg < steps; ++tg) issue_grad(tg, tg);
-    for (int tl = 0; tl < LA && tl < steps; ++tl) issue_rows(tl);
-
-    SumRing<K> vring;
-    vring.clear();
-    int gstage = 0;
-#pragma unroll 1
-    for (int t0 = 0; t0 < steps; t0 += PERIOD) {
-#pragma unroll
-        for (int q = 0; q < PERIOD; ++q) {
-            const int t = t0 + q;
-            const int slot = t & (NS - 1), hs = t & (kSplitHand - 1);
-            // ---- refill the slot of step t + LA (last used by step t + LA - NS), after finishing that step's sums
-            if (t >= NS - LA) {
-                const int ts = t - (NS - LA);
-                mbar_wait(&bars.empty[ts & (NS - 1)], (ts / NS) & 1);
-                reduce_step(ts);
-            }
-            if (t + LA < steps) issue_rows(t + LA);
-            // ---- A's step t
-            mbar_wait(&hfull[hs * SG::NCW], (t / kSplitHand) & 1);
-            if (t + GS < steps) issue_grad(t + GS, gstage);      // A is done with this stage
-            const int hr = t - (K - 1);
-            const bool has_cells = hr >= g_lo && hr < g_hi;
-            float a[4][4];
-            if (has_cells) {
-                const float *hd = hand + hs * (16 * NT);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4 *>(a[i]) = *reinterpret_cast<const float4 *>(hd + i * (4 * NT));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) a[i][j] = 0.f;
-            }
-            float va[4][4];
-            vring.step(q, a, va);
-            mbar_wait(&bars.full[slot], (t / NS) & 1);
-            float *S = smem + slot * G::SLOT;
-            float red[8];
-            {
-                float pt[PL];
-#pragma unroll
-                for (int v = 0; v < PL / 4; ++v)
-                    *reinterpret_cast<float4 *>(&pt[4 * v]) = *reinterpret_cast<const float4 *>(S + G::OFF_PROJT + pidx + 4 * v);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float pre[4], suf[4];
-                    pre[0] = va[0][j]; pre[1] = pre[0] + va[1][j]; pre[2] = pre[1] + va[2][j]; pre[3] = pre[2] + va[3][j];
-                    suf[3] = va[3][j]; suf[2] = suf[3] + va[2][j]; suf[1] = suf[2] + va[1][j]; suf[0] = pre[3];
-#pragma unroll
-                    for (int xi = 0; xi < K + 3; ++xi) {
-                        const float h = xi - (K - 1) <= 0 ? pre[xi < 3 ? xi : 3] : suf[xi - (K - 1)];
-                        red[xi] = j == 0 ? pt[xi + 3] * h : fmaf(pt[xi - j + 3], h, red[xi]);
-                    }
-                }
-#pragma unroll
-                for (int xi = K + 3; xi < 8; ++xi) red[xi] = 0.f;
-            }
-            // ---- cross-lane sums: T1 partials next to A's Bs / Am in this lane's scratch row, then lane l adds value #l
-            {
-                float *xp = xps + (t & 1) * SG::XPOSE_PAR;
-                *reinterpret_cast<float4 *>(xp + l16 * G::XPOSE_STRIDE) = make_float4(red[0], red[1], red[2], red[3]);
-                *reinterpret_cast<float4 *>(xp + l16 * G::XPOSE_STRIDE + 4) = make_float4(red[4], red[5], red[6], red[7]);
-                __syncwarp();
-                float part[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    part[m] = (xp[(4 * m) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 1) * G::XPOSE_STRIDE + l16]) +
-                              (xp[(4 * m + 2) * G::XPOSE_STRIDE + l16] + xp[(4 * m + 3) * G::XPOSE_STRIDE + l16]);
-                S[G::OFF_STG + u * 16 + l16] = (part[0] + part[1]) + (part[2] + part[3]);
-            }
-            __syncwarp();
-            if ((rt & 31) == 0) {
-                mbar_arrive(&hempty[hs * SG::NCW]);
-                mbar_arrive(&bars.empty[slot]);
-            }
-            gstage = gstage + 1 == GS ? 0 : gstage + 1;
-        }
-    }
-    for (int ts = steps - (NS - LA); ts < steps; ++ts) {
-        if (ts < 0) continue;
-        mbar_wait(&bars.empty[ts & (NS - 1)], (ts / NS) & 1);
-        reduce_step(ts);
-    }
-}
-
-template <int K, int NU, int WG, bool HG>
-__global__ void __launch_bounds__(2 * SplitGeom<K, NU, WG>::TPR, 1)
-    sliding_backward_split_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
-                                  const float *__restrict__ grad, const uint32_t tc_threshold, const HeadGrad hg) {
-    using F = SlideGeom<K, NU, WG>;
-    using SG = SplitGeom<K, NU, WG>;
-    constexpr int WTC = F::WTC, SC = F::SC, NS = F::NS, NCW = SG::NCW, NTHR = 2 * SG::TPR;
-    extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], hfull_bar[kSplitHand * NCW], hempty_bar[kSplitHand * NCW];
-
-    if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
-    const int tid = threadIdx.x;
-    const int wt = blockIdx.x / L.n_chunks, ch = blockIdx.x % L.n_chunks, nb = blockIdx.y, b = blockIdx.z;
-    const int w_base = wt * WTC, s_base = chunk_s_base(L, p.W, w_base, ch), h0 = nb * L.RB;
-    const int rows = min(L.RB, p.H - h0);
-    const int steps = (L.RBH + K - 1 + F::PERIOD - 1) / F::PERIOD * F::PERIOD;
-    float *T1tile = (float *)(ws + BL.off_T1) +
-                    (((((int64_t)b * L.n_chunks + ch) * 2 + (nb & 1)) * 2 + (wt & 1)) * BL.Hp + h0) * BL.Wp + w_base;
-    const int64_t prow = (((int64_t)b * L.n_chunks + ch) * L.NB * L.RB + h0) * L.cs_pitch + w_base;
-    float *AmRow = (float *)(ws + BL.off_Am) + prow, *BsRow = (float *)(ws + BL.off_Bs) + prow;
-    if (reinterpret_cast<const uint8_t *>(ws + L.off_flags)[tile_index(L, b, nb, wt, ch)]) {
-        for (int e = tid; e < BL.TH * BL.TW; e += NTHR) T1tile[(int64_t)(e / BL.TW) * BL.Wp + e % BL.TW] = 0.f;
-        for (int e = tid; e < rows * WTC; e += NTHR) {
-            AmRow[(int64_t)(e / WTC) * L.cs_pitch + e % WTC] = 0.f;
-            BsRow[(int64_t)(e / WTC) * L.cs_pitch + e % WTC] = 0.f;
-        }
-        return;
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            mbar_init(&full_bar[i], F::NCONS);      // one cp.async arrival per thread of group B
-            mbar_init(&empty_bar[i], F::NCW);       // one arrival per warp of group B
-        }
-        for (int i = 0; i < kSplitHand * NCW; ++i) {
-            mbar_init(&hfull_bar[i], 1);
-            mbar_init(&hempty_bar[i], 1);
-        }
-        mbar_fence_init();
-    }
-    // never-loaded regions must hold finite values (warm-up steps read stale statistics and multiply them by zero)
-    for (int i = tid; i < SG::SMEM_FLOATS / 4; i += NTHR) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int role = tid >= SG::TPR, rt = tid - role * SG::TPR;
-    if (rt >= F::NCONS) return;   // the idle lanes of each group's last warp
-    SplitBars bars{full_bar, empty_bar, hfull_bar, hempty_bar};
-
-    const bool vec = p.banded && (p.D & 3) == 0 && s_base + SC <= p.D;
-    const bool clean_left = w_base > 0 && w_base - (s_base + SC - 1) - (K / 2 + 3) >= 0;
-    const bool clean_right = w_base + WTC + K <= p.W;
-    const int mode = (vec && clean_left && w_base + WTC <= p.W) ? 0 : vec ? 1 : 2;
-    if (role == 0) {
-#define CUSTMA_SPLIT_A(MODE, DIR) \
-    split_role_a<K, NU, WG, MODE, DIR, HG>(p, smem, bars, rt, b, h0, rows, w_base, s_base, steps, grad, hg)
-        if (mode == 0) CUSTMA_SPLIT_A(0, 1);
-        else if (mode == 1 && clean_right) CUSTMA_SPLIT_A(1, 2);
-        else if (mode == 1) CUSTMA_SPLIT_A(1, 0);
-        else CUSTMA_SPLIT_A(2, 0);
-#undef CUSTMA_SPLIT_A
-    } else {
-        BwdRowLoader<K, NU, WG> loader;
-        loader.init(L, ws, b, nb, h0, w_base, s_base, rt);
-#define CUSTMA_SPLIT_B(MODE) \
-    split_role_b<K, NU, WG, MODE, HG>(p, L, smem, bars, loader, rt, b, h0, rows, w_base, s_base, steps, grad, hg, T1tile, \
-                                      BL.Wp, AmRow, BsRow)
-        if (mode == 0) CUSTMA_SPLIT_B(0);
-        else if (mode == 1) CUSTMA_SPLIT_B(1);
-        else CUSTMA_SPLIT_B(2);
-#undef CUSTMA_SPLIT_B
-    }
-}
-
 template <int K, int NU, int WG>
 static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLayout &BL, char *ws, const float *grad,
                           uint32_t thr, const HeadGrad &hg, cudaStream_t stream) {
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    static const bool split = getenv("CUSTMA_BWD_SINGLE") == nullptr;   // A/B switch while the split kernel is being measured
-    if (split) {
-        using SG = SplitGeom<K, NU, WG>;
-        auto kern = hg.state ? sliding_backward_split_kernel<K, NU, WG, true> : sliding_backward_split_kernel<K, NU, WG, false>;
-        CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::SMEM_BYTES));
-        kern<<<grid, 2 * SG::TPR, SG::SMEM_BYTES, stream>>>(p, L, BL, ws, grad, thr, hg);
-        CUSTMA_LAUNCH_CHECK("sliding_backward_split_kernel");
-        return CUSTMA_OK;
-    }
     const size_t smem = BwdGeom<K, NU, WG>::SMEM_BYTES;
     auto kern = hg.state ? sliding_backward_kernel<K, NU, WG, true> : sliding_backward_kernel<K, NU, WG, false>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
