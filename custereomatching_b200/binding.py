@@ -46,6 +46,7 @@ SYMBOLS = (
     "custma_backward_head",
     "custma_host_step",
     "custma_host_submit",
+    "custma_host_submit_u8",
     "custma_host_wait",
     "custma_host_release",
 )
@@ -101,6 +102,9 @@ def _declare(lib):
     lib.custma_host_submit.restype = ctypes.c_int
     lib.custma_host_submit.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32,
                                        ctypes.POINTER(ctypes.c_uint64)]
+    lib.custma_host_submit_u8.restype = ctypes.c_int
+    lib.custma_host_submit_u8.argtypes = [_ptr, _i32, _i32, _ptr, _i32, _i32, ctypes.c_float, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                          _i32, _i32, _i32, _i32, _i32, _u32, ctypes.POINTER(ctypes.c_uint64)]
     lib.custma_host_wait.restype = ctypes.c_int
     lib.custma_host_wait.argtypes = [ctypes.c_uint64]
     lib.custma_host_release.restype = ctypes.c_int
@@ -238,6 +242,18 @@ def host_submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volu
                                    cost_volume_dev or None, cost_volume_grad_dev or None, B, H, W, D, k, flags,
                                    ctypes.byref(ticket))
     check(rc, "custma_host_submit")
+    return int(ticket.value)
+
+
+def host_submit_u8(h_camera_u8, camera_channels, camera_channel, h_projector_u8, projector_channels, projector_channel,
+                   scale, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B, H, W, D, k, flags=0) -> int:
+    """custma_host_submit for interleaved uint8 host images; returns the ticket."""
+    ticket = ctypes.c_uint64(0)
+    rc = load().custma_host_submit_u8(h_camera_u8, camera_channels, camera_channel, h_projector_u8, projector_channels,
+                                      projector_channel, float(scale), h_best, h_index, h_camera_grad or None,
+                                      cost_volume_dev or None, cost_volume_grad_dev or None, B, H, W, D, k, flags,
+                                      ctypes.byref(ticket))
+    check(rc, "custma_host_submit_u8")
     return int(ticket.value)
 
 

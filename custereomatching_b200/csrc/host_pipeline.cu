@@ -21,6 +21,8 @@ struct Slot {
     int32_t *index = nullptr;
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    uint8_t *u8 = nullptr;          // staging of 8-bit host images (custma_host_submit_u8), grown on demand
+    size_t u8_bytes = 0;
 };
 
 struct HostCtx {
@@ -47,7 +49,7 @@ static void release_locked() {
         if (s.bwd_done) cudaEventDestroy(s.bwd_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
         cudaFree(s.cam); cudaFree(s.proj); cudaFree(s.best); cudaFree(s.grad); cudaFree(s.vol); cudaFree(s.index);
-        cudaFree(s.ws);
+        cudaFree(s.ws); cudaFree(s.u8);
         s = Slot();
     }
     for (auto &row : g_ctx.done)
@@ -129,15 +131,27 @@ int custma_host_release(void) {
     return CUSTMA_OK;
 }
 
-static int submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
+// how the host images of a submit are encoded: fp32 planes, or interleaved 8-bit images converted on the device
+struct HostImages {
+    const void *cam = nullptr, *proj = nullptr;
+    bool u8 = false;
+    int32_t cam_channels = 1, cam_channel = 0, proj_channels = 1, proj_channel = 0;
+    float scale = 1.f;
+};
+
+static int submit(const HostImages &img, float *h_best, int32_t *h_index,
                   float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                   int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool streamed, uint64_t *ticket) {
-    if (!h_camera || !h_projector || !h_best || !h_index)
+    if (!img.cam || !img.proj || !h_best || !h_index)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "h_camera, h_projector, h_best and h_index must not be NULL");
     if ((cost_volume_grad_dev != nullptr) != (h_camera_grad != nullptr))
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "h_camera_grad is required iff cost_volume_grad_dev is given");
     if (B <= 0 || H <= 0 || W <= 0 || D < 0 || k < 1 || k > CUSTMA_MAX_KERNEL_SIZE)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "bad shape B=%d H=%d W=%d D=%d k=%d", B, H, W, D, k);
+    if (img.u8 && (img.cam_channels < 1 || img.proj_channels < 1 || img.cam_channel < 0 || img.cam_channel >= img.cam_channels ||
+                   img.proj_channel < 0 || img.proj_channel >= img.proj_channels))
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "bad channel selection: camera %d of %d, projector %d of %d", img.cam_channel,
+                         img.cam_channels, img.proj_channel, img.proj_channels);
     std::lock_guard<std::mutex> lock(g_mutex);
     const int32_t chunk = pick_chunk(B, H, W, D, streamed);
     int rc = ensure_ctx(chunk, H, W, D, k, flags, cost_volume_dev == nullptr);
@@ -150,8 +164,26 @@ static int submit(const float *h_camera, const float *h_projector, float *h_best
         const size_t img_bytes = (size_t)nb * pix * sizeof(float);
         // the slot's result buffers are free once the device->host copies of its previous chunk are done
         CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.d2h_done, 0));
-        CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.cam, h_camera + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
-        CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.proj, h_projector + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
+        if (!img.u8) {
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.cam, (const float *)img.cam + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.proj, (const float *)img.proj + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            // 8-bit images cross PCIe as they are (a quarter of the bytes per channel) and become fp32 planes on the device
+            const size_t cb = (size_t)nb * pix * img.cam_channels, pb = (size_t)nb * pix * img.proj_channels;
+            const size_t need = align256(cb) + align256(pb);
+            if (s.u8_bytes < need) {
+                CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                cudaFree(s.u8);
+                s.u8 = nullptr; s.u8_bytes = 0;
+                CUSTMA_CUDA_CHECK(cudaMalloc(&s.u8, need));
+                s.u8_bytes = need;
+            }
+            uint8_t *dc = s.u8, *dp = s.u8 + align256(cb);
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dc, (const uint8_t *)img.cam + (size_t)b0 * pix * img.cam_channels, cb, cudaMemcpyHostToDevice, s.stream));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dp, (const uint8_t *)img.proj + (size_t)b0 * pix * img.proj_channels, pb, cudaMemcpyHostToDevice, s.stream));
+            if ((rc = custma_ingest_u8(dc, s.cam, nb, H, W, img.cam_channels, img.cam_channel, img.scale, s.stream))) return rc;
+            if ((rc = custma_ingest_u8(dp, s.proj, nb, H, W, img.proj_channels, img.proj_channel, img.scale, s.stream))) return rc;
+        }
         float *vol = cost_volume_dev ? cost_volume_dev + (size_t)b0 * pix * C : s.vol;
         rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags, s.ws, s.ws_bytes, s.stream);
         if (rc) return rc;
@@ -177,11 +209,30 @@ static int submit(const float *h_camera, const float *h_projector, float *h_best
     return CUSTMA_OK;
 }
 
+static HostImages fp32_images(const float *cam, const float *proj) {
+    HostImages img;
+    img.cam = cam; img.proj = proj;
+    return img;
+}
+
+int custma_host_submit_u8(const uint8_t *h_camera_u8, int32_t camera_channels, int32_t camera_channel,
+                          const uint8_t *h_projector_u8, int32_t projector_channels, int32_t projector_channel, float scale,
+                          float *h_best, int32_t *h_index, float *h_camera_grad, float *cost_volume_dev,
+                          const float *cost_volume_grad_dev, int32_t B, int32_t H, int32_t W, int32_t D, int32_t k,
+                          uint32_t flags, uint64_t *ticket) {
+    HostImages img;
+    img.cam = h_camera_u8; img.proj = h_projector_u8; img.u8 = true;
+    img.cam_channels = camera_channels; img.cam_channel = camera_channel;
+    img.proj_channels = projector_channels; img.proj_channel = projector_channel;
+    img.scale = scale;
+    return submit(img, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B, H, W, D, k, flags, true, ticket);
+}
+
 int custma_host_submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
                        float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                        int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, uint64_t *ticket) {
-    return submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B, H, W, D,
-                  k, flags, true, ticket);
+    return submit(fp32_images(h_camera, h_projector), h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev,
+                  B, H, W, D, k, flags, true, ticket);
 }
 
 int custma_host_wait(uint64_t ticket) {
@@ -203,8 +254,8 @@ int custma_host_step(const float *h_camera, const float *h_projector, float *h_b
                      float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                      int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
     uint64_t t = 0;
-    const int rc = submit(h_camera, h_projector, h_best, h_index, h_camera_grad, cost_volume_dev, cost_volume_grad_dev, B,
-                          H, W, D, k, flags, false, &t);
+    const int rc = submit(fp32_images(h_camera, h_projector), h_best, h_index, h_camera_grad, cost_volume_dev,
+                          cost_volume_grad_dev, B, H, W, D, k, flags, false, &t);
     return rc ? rc : custma_host_wait(0);
 }
 

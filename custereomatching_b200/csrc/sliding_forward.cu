@@ -353,8 +353,7 @@ static int launch_k(const SlidingConfig &cfg, const Problem &p, const SlidingLay
     switch (cfg.NU) {
         case 1: return launch_cfg<K, 1, 12>(p, L, ws, cost, keys, thr, head, stream);
         case 2: return launch_cfg<K, 2, 6>(p, L, ws, cost, keys, thr, head, stream);
-        case 3: return cfg.WG == 5 ? launch_cfg<K, 3, 5>(p, L, ws, cost, keys, thr, head, stream)
-                                   : launch_cfg<K, 3, 4>(p, L, ws, cost, keys, thr, head, stream);
+        case 3: return launch_cfg<K, 3, 4>(p, L, ws, cost, keys, thr, head, stream);
         default: return launch_cfg<K, 4, 3>(p, L, ws, cost, keys, thr, head, stream);
     }
 }

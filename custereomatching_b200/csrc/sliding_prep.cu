@@ -31,8 +31,6 @@ bool sliding_pick_config(const Problem &p, bool backward, SlidingConfig *cfg) {
         // forward: 6 warps (168 registers) per CTA, two CTAs per SM so that one CTA's start-up hides behind the other
         const int wg[5] = {0, 12, 6, 4, 3};
         cfg->WG = wg[cfg->NU];
-        static const bool wg5 = getenv("CUSTMA_FWD_WG5") != nullptr;   // experiment: 15 warps per SM at 128 registers
-        if (wg5 && cfg->NU == 3) cfg->WG = 5;
     } else {
         // backward: two register rings per cell (window sum + vertical sum of a) need ~250 registers: one CTA of
         // at most 256 threads per SM, so NU * WG <= 16

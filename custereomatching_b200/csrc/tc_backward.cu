@@ -95,6 +95,17 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// the MMA-issuing warp waits for a whole operand build: poll slowly and leave its scheduler's issue slots to the four
+// worker warps that share it (ncu r01: 15 % of all executed instructions were these spin loops)
+__device__ __forceinline__ void bar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t *r, uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -156,7 +167,7 @@ __device__ __forceinline__ float build_patch(const float *ring, int pitch, int y
 #pragma unroll
         for (int j = 0; j < KW; ++j) { v[i * KW + j] = src[j]; sum += v[i * KW + j]; }
     }
-    const float mean = sum / (float)NTAP;
+    const float mean = sum * (1.f / (float)NTAP);
     float q = 0.f;
 #pragma unroll
     for (int t = 0; t < 4 * CHW; ++t) {
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             const int rows = min(RB, H - nb * RB);
             for (int r = 0; r < rows; ++r)
                 for (int blk = 0; blk < nblk; ++blk, ++J) {
-                    bar_wait(smem_u32(&S.ops1_bar), J & 1);
+                    bar_wait_backoff(smem_u32(&S.ops1_bar), J & 1);
                     fence_after();
                     if (lane == 0) {
                         uint32_t acc = 0;
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                         commit(smem_u32(&S.mma1_bar));
                     }
                     __syncwarp();
-                    bar_wait(smem_u32(&S.ops2_bar), J & 1);
+                    bar_wait_backoff(smem_u32(&S.ops2_bar), J & 1);
                     fence_after();
                     if (lane == 0) {
                         uint32_t acc = blk == 0 ? 0u : 1u;
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int i = i0 + 4 * g + k;
-                                const float rs = rsqrtf(fmaf(e2, ee[k], kEps));
+                                const float rs = rsqrt_fast(fmaf(e2, ee[k], kEps));
                                 float a = gg[k] * rs;                               // g / den; g is 0 where the cell does not exist
                                 if (p_first - i < 0) a = 0.f;                       // off-image projector column: constant cost
                                 // what is left of a*mu - b (mu = exy / ex2, see the row epilogue): a * (exy - ex2*ey2) / den^2

@@ -175,6 +175,16 @@ int custma_host_step(const float *h_camera, const float *h_projector, float *h_b
 int custma_host_submit(const float *h_camera, const float *h_projector, float *h_best, int32_t *h_index,
                        float *h_camera_grad, float *cost_volume_dev, const float *cost_volume_grad_dev, int32_t B,
                        int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, uint64_t *ticket);
+/* custma_host_submit for 8-bit host images (examples/verify.py:138-142,149: cv2.imread gives uint8 [H,W,channels]; the
+ * reference divides by 255 and takes channel 0 on the host).  The interleaved uint8 images [B,H,W,channels] cross PCIe as
+ * they are - a quarter of the fp32 bytes per channel - and custma_ingest_u8 turns the selected channel into the fp32
+ * plane (value * scale) on the device, inside the same stream as the kernels.  camera_grad is the gradient with respect
+ * to that fp32 plane. */
+int custma_host_submit_u8(const uint8_t *h_camera_u8, int32_t camera_channels, int32_t camera_channel,
+                          const uint8_t *h_projector_u8, int32_t projector_channels, int32_t projector_channel, float scale,
+                          float *h_best, int32_t *h_index, float *h_camera_grad, float *cost_volume_dev,
+                          const float *cost_volume_grad_dev, int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size,
+                          uint32_t flags, uint64_t *ticket);
 int custma_host_wait(uint64_t ticket);
 /* Releases the device/stream resources custma_host_step caches between calls. */
 int custma_host_release(void);
