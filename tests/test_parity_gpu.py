@@ -930,3 +930,23 @@ def test_projector_gradient_through_autograd_and_batches():
     cv = custma.stereo_matching(c2, p2, 0, k)
     cv.backward(torch.ones_like(cv))
     assert p2.grad is None
+
+
+def test_host_submit_u8_equals_ingest_then_device_path():
+    """custma_host_submit_u8: 8-bit interleaved host images in (RGB camera, channel 0; gray projector), same results as
+    ingesting on the device and calling the kernels directly."""
+    from custereomatching_b200 import binding
+    B, H, W, D, k = 2, 40, 200, 64, 5
+    rng = np.random.RandomState(12)
+    cam_u8 = torch.from_numpy(rng.randint(0, 256, size=(B, H, W, 3)).astype(np.uint8)).pin_memory()
+    proj_u8 = torch.from_numpy(rng.randint(0, 256, size=(B, H, W)).astype(np.uint8)).pin_memory()
+    g = dev(rng.randn(B, H, W, D).astype(np.float32))
+    hb, hi, hg = torch.empty(B, H, W).pin_memory(), torch.empty(B, H, W, dtype=torch.int32).pin_memory(), torch.empty(B, H, W).pin_memory()
+    t = binding.host_submit_u8(cam_u8.data_ptr(), 3, 0, proj_u8.data_ptr(), 1, 0, 1.0 / 255.0, hb.data_ptr(), hi.data_ptr(),
+                               hg.data_ptr(), 0, g.data_ptr(), B, H, W, D, k)
+    binding.host_wait(t)
+    cam, proj = cb.ingest_u8(cam_u8.cuda(), 0), cb.ingest_u8(proj_u8.cuda())
+    best, disp = cb.wta(cam, proj, D, k)
+    grad = cb.backward(g, cam, proj, k, D)
+    assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp) and torch.equal(hg.cuda(), grad)
+    binding.host_release()
