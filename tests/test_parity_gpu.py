@@ -945,7 +945,7 @@ def test_host_submit_u8_equals_ingest_then_device_path():
     t = binding.host_submit_u8(cam_u8.data_ptr(), 3, 0, proj_u8.data_ptr(), 1, 0, 1.0 / 255.0, hb.data_ptr(), hi.data_ptr(),
                                hg.data_ptr(), 0, g.data_ptr(), B, H, W, D, k)
     binding.host_wait(t)
-    cam, proj = cb.ingest_u8(cam_u8.cuda(), 0), cb.ingest_u8(proj_u8.cuda())
+    cam, proj = cb.ingest_u8(cam_u8.cuda(), 0), cb.ingest_u8(proj_u8.cuda().unsqueeze(-1))   # [B,H,W,1]: a 3-D tensor is [H,W,Ch]
     best, disp = cb.wta(cam, proj, D, k)
     grad = cb.backward(g, cam, proj, k, D)
     assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp) and torch.equal(hg.cuda(), grad)
