@@ -1,6 +1,7 @@
 // C-ABI entry points of libcustma_b200.so (see include/custma_b200.h): argument validation, workspace layout,
 // dispatch between the sliding-window kernels and the direct two-pass kernels.
 #include <stdarg.h>
+#include <algorithm>
 #include <atomic>
 #include <stdio.h>
 #include <string.h>
@@ -248,10 +249,55 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
 }
 
 // ---- gradient with respect to the projector image (the reference returns None for it) -----------
+// ZNCC is symmetric in its two patches.  Two routes:
+//   direct   direct_patch_grad_kernel<SWAP> (direct.cu): a warp per projector pixel, O(k^2) per cell, every k
+//   fast     (banded volume, odd k with a sliding-window backward, i.e. k = 3 or 5) the camera-gradient kernels on the
+//            mirrored, role-exchanged problem: camera' = flip_x(projector), projector' = flip_x(camera) - mirroring
+//            turns "projector column = camera column + s" into "- s", which is what the banded kernels index - with the
+//            upstream gradient sheared accordingly, g'[h, c', s] = g[h, W-1-c'+s, s] (a bijection between the valid
+//            cells of the two volumes), and projector_grad = flip_x(camera_grad').  Costs one extra pass over the
+//            gradient (read once, written once into the workspace) next to the O(1)-per-cell backward.
+__global__ void __launch_bounds__(256)
+    flip_images_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ a_out,
+                       float *__restrict__ b_out, int64_t rows, int W) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * W) return;
+    const int64_t r = i / W;
+    const int x = (int)(i - r * W);
+    a_out[i] = a[r * W + (W - 1 - x)];
+    if (b) b_out[i] = b[r * W + (W - 1 - x)];
+}
+
+constexpr int kShearPitch = 34;   // (pitch + 1) odd: the diagonal reads of the tile hit 32 different banks
+__global__ void __launch_bounds__(256)
+    shear_gradient_kernel(const float *__restrict__ g, float *__restrict__ gs, int W, int D) {
+    __shared__ float tile[63][kShearPitch];
+    const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t plane = (int64_t)blockIdx.z * W * D;
+    const int w_lo = W - 1 - (c0 + 31) + s0, s = s0 + tx;
+    for (int r = ty; r < 63; r += 8) {
+        const int w = w_lo + r;
+        tile[r][tx] = (w >= 0 && w < W && s < D) ? __ldcs(g + plane + (int64_t)w * D + s) : 0.f;
+    }
+    __syncthreads();
+    for (int cy = ty; cy < 32; cy += 8) {
+        const int c = c0 + cy;
+        if (c < W && s < D) {
+            const int w = W - 1 - c + s;                       // row of the source cell; beyond the image: no cell
+            __stcs(gs + plane + (int64_t)c * D + s, w < W ? tile[31 - cy + tx][tx] : 0.f);
+        }
+    }
+}
+
+static bool projector_fast_path(const Problem &p, uint32_t flags) {
+    return !(flags & CUSTMA_FLAG_DIRECT) && p.banded && (p.k & 1) && sliding_backward_supported(p);
+}
+
 size_t custma_backward_projector_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
     Problem p;
     if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
-    (void)flags;
+    if (projector_fast_path(p, flags))
+        return backward_ws(p, 0) + align256((size_t)p.cells() * sizeof(float)) + 3 * align256((size_t)p.pixels() * sizeof(float));
     return stats_bytes(p) + align256((size_t)p.pixels() * p.k * p.k * sizeof(float));
 }
 
@@ -269,8 +315,41 @@ int custma_backward_projector(const float *cost_volume_grad, const float *camera
         return rc;
     if ((rc = check_device())) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t need = custma_backward_projector_workspace_bytes(B, H, W, D, k, flags);
+    if (projector_fast_path(p, flags)) {
+        if (!workspace || workspace_bytes < need)
+            return set_error(CUSTMA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace ? workspace_bytes : (size_t)0);
+        if (((uintptr_t)workspace & 255) != 0) return set_error(CUSTMA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+        char *base = (char *)workspace;
+        const size_t bws = backward_ws(p, 0), img = align256((size_t)p.pixels() * sizeof(float));
+        float *gs = (float *)(base + bws);
+        float *camF = (float *)(base + bws + align256((size_t)p.cells() * sizeof(float)));
+        float *projF = (float *)((char *)camF + img), *gradF = (float *)((char *)projF + img);
+        const int64_t rows = (int64_t)B * H;
+        const unsigned fb = (unsigned)((rows * W + 255) / 256);
+        // camera' = mirrored projector, projector' = mirrored camera
+        flip_images_kernel<<<fb, 256, 0, stream>>>(projector, camera, camF, projF, rows, W);
+        CUSTMA_LAUNCH_CHECK("flip_images_kernel");
+        if (rows > 65535 * 1ll) {   // gridDim.z limit: one launch per slab of image rows
+            for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+                const int64_t nr = std::min<int64_t>(65535, rows - r0);
+                shear_gradient_kernel<<<dim3((D + 31) / 32, (W + 31) / 32, (unsigned)nr), dim3(32, 8), 0, stream>>>(
+                    cost_volume_grad + r0 * W * D, gs + r0 * W * D, W, D);
+                CUSTMA_LAUNCH_CHECK("shear_gradient_kernel");
+            }
+        } else {
+            shear_gradient_kernel<<<dim3((D + 31) / 32, (W + 31) / 32, (unsigned)rows), dim3(32, 8), 0, stream>>>(cost_volume_grad, gs, W, D);
+            CUSTMA_LAUNCH_CHECK("shear_gradient_kernel");
+        }
+        StatsPtrs s;
+        if ((rc = carve_stats(p, workspace, bws, bws, &s))) return rc;
+        if ((rc = launch_sliding_backward(p, gs, camF, projF, gradF, s.rest, s.rest_bytes, false, stream))) return rc;
+        flip_images_kernel<<<fb, 256, 0, stream>>>(gradF, nullptr, projector_grad, nullptr, rows, W);
+        CUSTMA_LAUNCH_CHECK("flip_images_kernel");
+        return CUSTMA_OK;
+    }
     StatsPtrs s;
-    if ((rc = carve_stats(p, workspace, workspace_bytes, custma_backward_projector_workspace_bytes(B, H, W, D, k, flags), &s))) return rc;
+    if ((rc = carve_stats(p, workspace, workspace_bytes, need, &s))) return rc;
     if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
     if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     return launch_direct_backward_projector(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,

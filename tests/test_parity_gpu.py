@@ -904,12 +904,31 @@ def test_projector_gradient_vs_oracle_autograd(H, W, D, k):
     assert_grad_close(out.cpu().numpy(), ref)
     again = cb.backward_projector(dev(g), dev(cam), dev(proj), k, D)
     assert torch.equal(out, again)                                   # deterministic: no atomics
+    # both routes: the default (banded, k = 3 / 5: sliding-window kernels on the mirrored problem) and the direct kernels
+    direct = cb.backward_projector(dev(g), dev(cam), dev(proj), k, D, flags=cb.FLAG_DIRECT)
+    assert_grad_close(direct.cpu().numpy(), ref)
     # symmetry that the kernel exploits: for the reference-shaped volume, the projector gradient is the camera gradient
     # of the transposed problem
     if D == 0:
         gt = np.ascontiguousarray(g.transpose(0, 2, 1))
         sym = cb.backward(dev(gt), dev(proj), dev(cam), k, 0, flags=cb.FLAG_DIRECT)
         assert_grad_close(out.cpu().numpy(), sym.cpu().numpy(), 1e-6)
+
+
+def test_projector_gradient_fast_path_on_larger_shapes():
+    """Several column tiles, row bands and a batch through the mirrored sliding-window route, against the direct kernels
+    (themselves checked against fp64 autograd above) and the oracle on one pair."""
+    for B, H, W, D, k in [(2, 90, 300, 64, 5), (1, 70, 420, 192, 3), (3, 40, 131, 96, 5)]:
+        cam, proj = rand_pair(H, W, seed=H + W, B=B)
+        g = torch.from_numpy(np.random.RandomState(2).randn(B, H, W, D).astype(np.float32)).cuda()
+        fast = cb.backward_projector(g, dev(cam), dev(proj), k, D)
+        direct = cb.backward_projector(g, dev(cam), dev(proj), k, D, flags=cb.FLAG_DIRECT)
+        assert_grad_close(fast.cpu().numpy(), direct.cpu().numpy())
+        valid = (np.arange(W)[:, None] - np.arange(D)[None, :]) >= 0
+        ref = zo.projector_grad_autograd(cam[0], proj[0], g[0].cpu().numpy() * valid, D, k).numpy()
+        assert_grad_close(fast[0].cpu().numpy(), ref)
+        one = cb.backward_projector(g[0].contiguous(), dev(cam[0]), dev(proj[0]), k, D)
+        assert torch.equal(one, fast[0])
 
 
 def test_projector_gradient_through_autograd_and_batches():

@@ -67,3 +67,9 @@ timed(fused_fwd, "fused head forward (no volume)")
 timed(fused_fwd_bwd, "fused head forward + backward (no volume)")
 timed(lambda: unfused(False), "volume + torch soft-argmax + mask, forward")
 timed(lambda: unfused(True), "volume + torch soft-argmax + mask, forward + backward")
+
+# projector gradient: the mirrored sliding-window route against the direct kernels
+gvol = torch.randn(P, H, W, D, device="cuda", generator=g)
+timed(lambda: cb.backward_projector(gvol, cam, proj, k, D), "projector gradient, mirrored sliding-window route")
+timed(lambda: cb.backward_projector(gvol, cam, proj, k, D, flags=cb.FLAG_DIRECT), "projector gradient, direct kernels")
+timed(lambda: cb.backward(gvol, cam, proj, k, D), "camera gradient (for comparison)")
