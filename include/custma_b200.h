@@ -120,8 +120,10 @@ int custma_backward_rows(const float *cost_volume_grad, const float *camera, con
 
 /* Gradient of sum(cost_volume * cost_volume_grad) with respect to the PROJECTOR image.  The reference has none
  * (custma/stereo_matching_wrapper.py:33 returns None); ZNCC is symmetric in its two patches, so this is the camera
- * gradient's arithmetic (custma/src/stereo_matching_kernel.cu:75-179) with the two images' roles exchanged.  Runs on the
- * direct two-pass kernels for every kernel_size (no sliding-window variant yet); deterministic, no atomics. */
+ * gradient's arithmetic (custma/src/stereo_matching_kernel.cu:75-179) with the two images' roles exchanged.  Default:
+ * for a banded volume and kernel_size 3 or 5 the sliding-window backward runs on the mirrored, role-exchanged problem
+ * (the workspace then also holds a sheared copy of the gradient, i.e. it is volume-sized); CUSTMA_FLAG_DIRECT, or any
+ * other shape, uses the direct two-pass kernels (every kernel_size, image-sized workspace).  Deterministic, no atomics. */
 size_t custma_backward_projector_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size,
                                                  uint32_t flags);
 int custma_backward_projector(const float *cost_volume_grad, const float *camera, const float *projector,
