@@ -37,11 +37,19 @@ struct HostCtx {
     cudaEvent_t done[kTickets][kSlots] = {};           // done[t % kTickets][s]: slot s has delivered everything of ticket t
 };
 
-static HostCtx g_ctx;
+// Two contexts are kept (least recently used one is rebuilt): a caller that alternates between two shapes - or two
+// devices - does not tear its streams and buffers down on every call.  A ticket carries its context in the top byte.
+constexpr int kContexts = 2;
+static HostCtx g_ctxs[kContexts];
+static uint64_t g_use_stamp[kContexts] = {};
+static uint64_t g_stamp = 0;
 static std::mutex g_mutex;
 
-static void release_locked() {
+static void release_locked(HostCtx &g_ctx) {
     if (!g_ctx.live) return;
+    int restore = -1;
+    cudaGetDevice(&restore);
+    cudaSetDevice(g_ctx.device);
     for (Slot &s : g_ctx.slot) {
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         if (s.d2h) { cudaStreamSynchronize(s.d2h); cudaStreamDestroy(s.d2h); }
@@ -56,6 +64,7 @@ static void release_locked() {
         for (cudaEvent_t &e : row)
             if (e) cudaEventDestroy(e);
     g_ctx = HostCtx();
+    if (restore >= 0) cudaSetDevice(restore);
 }
 
 // Pairs per pipelined chunk.  A synchronous step cuts the batch in two so that the copies of one half overlap the
@@ -77,7 +86,8 @@ static int32_t pick_chunk(int32_t B, int32_t H, int32_t W, int32_t D, bool strea
 // Builds every stream, event and buffer of the context.  g_ctx.live is set first so that release_locked() can take a
 // half-built context apart; ensure_ctx() does exactly that when anything here fails, so a later call never finds a
 // context that passes the cache test with null buffers in it.
-static int build_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume, int dev) {
+static int build_ctx(HostCtx &g_ctx, int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags,
+                     bool need_volume, int dev) {
     const int32_t C = D > 0 ? D : W;
     const size_t pair_vol = (size_t)H * W * C * sizeof(float);
     g_ctx.live = true; g_ctx.device = dev; g_ctx.H = H; g_ctx.W = W; g_ctx.D = D; g_ctx.k = k; g_ctx.flags = flags;
@@ -104,19 +114,43 @@ static int build_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, 
     return CUSTMA_OK;
 }
 
-static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume) {
+static bool ctx_matches(const HostCtx &c, int dev, int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags,
+                        bool need_volume) {
+    return c.live && c.device == dev && c.H == H && c.W == W && c.D == D && c.k == k && c.flags == flags &&
+           c.chunk >= chunk && (c.with_volume || !need_volume);
+}
+
+// index of a context built for these arguments (reused, or built in the free / least recently used entry), < 0 on error
+static int ensure_ctx(int32_t chunk, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags, bool need_volume, int *index) {
     int dev = 0;
     CUSTMA_CUDA_CHECK(cudaGetDevice(&dev));
-    if (g_ctx.live && g_ctx.device == dev && g_ctx.H == H && g_ctx.W == W && g_ctx.D == D && g_ctx.k == k &&
-        g_ctx.flags == flags && g_ctx.chunk >= chunk && (g_ctx.with_volume || !need_volume))
-        return CUSTMA_OK;
-    release_locked();
-    const int rc = build_ctx(chunk, H, W, D, k, flags, need_volume, dev);
-    if (rc != CUSTMA_OK) {
-        release_locked();          // e.g. out of memory on the volume buffer: leave no half-built context behind
-        cudaGetLastError();        // and no sticky allocation error for the caller's next CUDA call
+    int pick = -1;
+    for (int i = 0; i < kContexts; ++i)
+        if (ctx_matches(g_ctxs[i], dev, chunk, H, W, D, k, flags, need_volume)) pick = i;
+    if (pick < 0) {
+        // same device and shape but too small (chunk / volume): rebuild that one; else a free entry; else the oldest
+        for (int i = 0; i < kContexts && pick < 0; ++i) {
+            const HostCtx &c = g_ctxs[i];
+            if (c.live && c.device == dev && c.H == H && c.W == W && c.D == D && c.k == k && c.flags == flags) pick = i;
+        }
+        for (int i = 0; i < kContexts && pick < 0; ++i)
+            if (!g_ctxs[i].live) pick = i;
+        if (pick < 0) {
+            pick = 0;
+            for (int i = 1; i < kContexts; ++i)
+                if (g_use_stamp[i] < g_use_stamp[pick]) pick = i;
+        }
+        release_locked(g_ctxs[pick]);
+        const int rc = build_ctx(g_ctxs[pick], chunk, H, W, D, k, flags, need_volume, dev);
+        if (rc != CUSTMA_OK) {
+            release_locked(g_ctxs[pick]);   // e.g. out of memory on the volume buffer: leave no half-built context behind
+            cudaGetLastError();             // and no sticky allocation error for the caller's next CUDA call
+            return rc;
+        }
     }
-    return rc;
+    g_use_stamp[pick] = ++g_stamp;
+    *index = pick;
+    return CUSTMA_OK;
 }
 
 }  // namespace custma
@@ -127,7 +161,7 @@ extern "C" {
 
 int custma_host_release(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
-    release_locked();
+    for (HostCtx &c : g_ctxs) release_locked(c);
     return CUSTMA_OK;
 }
 
@@ -154,8 +188,10 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
                          img.cam_channels, img.proj_channel, img.proj_channels);
     std::lock_guard<std::mutex> lock(g_mutex);
     const int32_t chunk = pick_chunk(B, H, W, D, streamed);
-    int rc = ensure_ctx(chunk, H, W, D, k, flags, cost_volume_dev == nullptr);
+    int ci = -1;
+    int rc = ensure_ctx(chunk, H, W, D, k, flags, cost_volume_dev == nullptr, &ci);
     if (rc) return rc;
+    HostCtx &g_ctx = g_ctxs[ci];
     const int32_t C = D > 0 ? D : W;
     const size_t pix = (size_t)H * W;
     for (int32_t b0 = 0; b0 < B; b0 += chunk, g_ctx.next_slot = (g_ctx.next_slot + 1) % kSlots) {
@@ -205,7 +241,7 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
     }
     const uint64_t t = g_ctx.next_ticket++;
     for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventRecord(g_ctx.done[t % kTickets][i], g_ctx.slot[i].d2h));
-    if (ticket) *ticket = t;
+    if (ticket) *ticket = ((uint64_t)(ci + 1) << 56) | t;
     return CUSTMA_OK;
 }
 
@@ -237,16 +273,23 @@ int custma_host_submit(const float *h_camera, const float *h_projector, float *h
 
 int custma_host_wait(uint64_t ticket) {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (!g_ctx.live) return CUSTMA_OK;
-    if (ticket == 0 || ticket >= g_ctx.next_ticket || ticket + kTickets <= g_ctx.next_ticket) {
-        // everything submitted so far (also for tickets whose events have been reused: later work completes later)
-        for (Slot &s : g_ctx.slot) {
+    const int ci = (int)(ticket >> 56) - 1;
+    const uint64_t seq = ticket & (((uint64_t)1 << 56) - 1);
+    if (ticket != 0 && ci >= 0 && ci < kContexts) {
+        HostCtx &c = g_ctxs[ci];
+        if (c.live && seq != 0 && seq < c.next_ticket && seq + kTickets > c.next_ticket) {
+            for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventSynchronize(c.done[seq % kTickets][i]));
+            return CUSTMA_OK;
+        }
+    }
+    // 0, an unknown ticket, or one whose events have been reused (later work completes later): everything submitted so far
+    for (HostCtx &c : g_ctxs) {
+        if (!c.live) continue;
+        for (Slot &s : c.slot) {
             CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
             CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
         }
-        return CUSTMA_OK;
     }
-    for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventSynchronize(g_ctx.done[ticket % kTickets][i]));
     return CUSTMA_OK;
 }
 

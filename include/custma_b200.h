@@ -188,7 +188,8 @@ int custma_host_submit_u8(const uint8_t *h_camera_u8, int32_t camera_channels, i
                           const float *cost_volume_grad_dev, int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size,
                           uint32_t flags, uint64_t *ticket);
 int custma_host_wait(uint64_t ticket);
-/* Releases the device/stream resources custma_host_step caches between calls. */
+/* Releases the device/stream resources the host entry points cache between calls (streams, events, image / result /
+ * volume buffers and workspaces for the two most recently used (device, shape, flags) combinations). */
 int custma_host_release(void);
 
 #ifdef __cplusplus

@@ -252,6 +252,26 @@ def test_host_submit_and_wait_stream_batches():
     binding.host_release()
 
 
+def test_host_entry_points_keep_two_shapes_alive():
+    """Alternating between two shapes must not invalidate tickets of the other shape (the host
+    context used to be a single global that a second shape tore down)."""
+    from custereomatching_b200 import binding
+    shapes = [(2, 30, 120, 32, 5), (1, 44, 90, 16, 3)]
+    work = []
+    for i, (B, H, W, D, k) in enumerate(shapes * 2):
+        cam, proj = rand_pair(H, W, seed=70 + i, B=B)
+        c, p_ = torch.from_numpy(cam).pin_memory(), torch.from_numpy(proj).pin_memory()
+        hb, hi = torch.empty(B, H, W).pin_memory(), torch.empty(B, H, W, dtype=torch.int32).pin_memory()
+        t = binding.host_submit(c.data_ptr(), p_.data_ptr(), hb.data_ptr(), hi.data_ptr(), 0, 0, 0, B, H, W, D, k)
+        work.append((t, c, p_, hb, hi, D, k))
+    for t, c, p_, hb, hi, D, k in work:
+        binding.host_wait(t)
+        best, disp = cb.wta(c.cuda(), p_.cuda(), D, k)
+        assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp)
+    binding.host_wait(0)
+    binding.host_release()
+
+
 def test_error_behaviour():
     cam = torch.rand(16, 16, device="cuda")
     with pytest.raises(RuntimeError, match="camera must be contiguous"):
