@@ -12,6 +12,7 @@ except ImportError as _e:  # no Python or CPU stand-in exists for it
 from .stereo_matching_wrapper import stereo_matching
 from .utils import Timer
 from .stereo_matching_wrapper import (stereo_matching_banded, stereo_matching_wta, stereo_matching_with_wta,
-                                      cost_volume_mask)
+                                      stereo_matching_masked, stereo_matching_soft_disparity,
+                                      stereo_matching_projector_grad, cost_volume_mask)
 
 __all__ = [k for k in globals().keys() if not k.startswith("_")]

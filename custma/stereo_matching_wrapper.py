@@ -51,6 +51,28 @@ def stereo_matching_with_wta(camera_image: torch.Tensor, projector_image: torch.
     return _F.cost_volume_and_wta(camera_image, projector_image, D, kernel_size)
 
 
+def stereo_matching_masked(camera_image: torch.Tensor, projector_image: torch.Tensor, D: int, kernel_size: int,
+                           threshold: float = 0.6):
+    """(best, index, mask, masked_disparity): examples/verify.py:72-74 and examples/test.py:78-84 in one fused call -
+    mask = best > threshold, masked_disparity = (column - correspondence) * mask; no volume is materialised."""
+    return _F.wta_masked(camera_image, projector_image, D, kernel_size, threshold)
+
+
+def stereo_matching_soft_disparity(camera_image: torch.Tensor, projector_image: torch.Tensor, D: int, kernel_size: int,
+                                   beta: float = 50.0, threshold: float = 0.6):
+    """(soft_disparity * mask, best, index, mask), differentiable w.r.t. the camera image: the soft_argmax of
+    examples/verify.py:31-39 (softargmax_beta = 50, :11) as the disparity of examples/test.py:85-86, fused into the
+    kernels - forward and backward never materialise the cost volume.  kernel_size 3 or 5."""
+    return _F.soft_disparity(camera_image, projector_image, D, kernel_size, beta, threshold)
+
+
+def stereo_matching_projector_grad(cost_volume_grad: torch.Tensor, camera_image: torch.Tensor,
+                                   projector_image: torch.Tensor, D: int, kernel_size: int) -> torch.Tensor:
+    """Gradient with respect to the projector image (the reference returns None for it,
+    custma/stereo_matching_wrapper.py:33)."""
+    return _F.backward_projector(cost_volume_grad, camera_image, projector_image, kernel_size, D)
+
+
 def cost_volume_mask(best: torch.Tensor, threshold: float = 0.6) -> torch.Tensor:
     """examples/verify.py:13,74."""
     return _F.confidence_mask(best, threshold)

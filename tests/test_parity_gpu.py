@@ -989,3 +989,19 @@ def test_host_submit_u8_equals_ingest_then_device_path():
     grad = cb.backward(g, cam, proj, k, D)
     assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp) and torch.equal(hg.cuda(), grad)
     binding.host_release()
+
+
+def test_custma_package_exports_the_fused_callers():
+    """The drop-in package also carries the example-level callers (mask, soft disparity head, projector gradient)."""
+    H, W, D, k = 24, 90, 32, 5
+    cam, proj = _matched_pair(H, W, seed=4)
+    b, i, m, md = custma.stereo_matching_masked(dev(cam), dev(proj), D, k)
+    b2, i2, m2, md2 = cb.wta_masked(dev(cam), dev(proj), D, k)
+    assert torch.equal(b, b2) and torch.equal(i, i2) and torch.equal(m, m2) and torch.equal(md, md2)
+    c = dev(cam).requires_grad_(True)
+    soft, best, idx, mask = custma.stereo_matching_soft_disparity(c, dev(proj), D, k)
+    soft.sum().backward()
+    assert c.grad is not None and torch.isfinite(c.grad).all() and torch.equal(best, b)
+    g = torch.randn(H, W, D, device="cuda")
+    pg = custma.stereo_matching_projector_grad(g, dev(cam), dev(proj), D, k)
+    assert torch.equal(pg, cb.backward_projector(g, dev(cam), dev(proj), k, D))
