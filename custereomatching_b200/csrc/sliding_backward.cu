@@ -479,11 +479,15 @@ __device__ __forceinline__ int div_near(int x, int d, int q0) {   // q0 * d <= x
     return q;
 }
 
-template <int K>
+// ONE: the volume has a single disparity chunk per column tile (banded, D <= 256 - every BASELINE config but the 8K pair):
+// the sums over chunks disappear at compile time (the generic loops were unrolled 16 times by the compiler and paid
+// their set-up on every one of the six places they appear in)
+template <int K, bool ONE>
 __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad, const uint32_t tc_threshold) {
     if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
+    const int n_chunks = ONE ? 1 : L.n_chunks;
     constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinRows + K - 1;
     // q1 = Am - Bs*A and q2 = Bs of the cells around the block; R* = their horizontal k-sums per (cell row, pixel column)
     __shared__ float q1[SH][SW + 1], q2[SH][SW + 1];
@@ -492,12 +496,12 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
     const int tid = threadIdx.y * kFinTX + threadIdx.x;
     // block-uniform bases (64-bit once); per-thread offsets stay 32-bit (every image of one pair is < 2^31 floats)
     const int chunk_stride = L.NB * L.RB * L.cs_pitch;                      // Am / Bs: [B][n_chunks][NB*RB][cs_pitch]
-    const float *Am = (const float *)(ws + BL.off_Am) + (int64_t)b * L.n_chunks * chunk_stride;
-    const float *Bs = (const float *)(ws + BL.off_Bs) + (int64_t)b * L.n_chunks * chunk_stride;
+    const float *Am = (const float *)(ws + BL.off_Am) + (int64_t)b * n_chunks * chunk_stride;
+    const float *Bs = (const float *)(ws + BL.off_Bs) + (int64_t)b * n_chunks * chunk_stride;
     const float *A = (const float *)(ws + L.off_A) + (int64_t)b * chunk_stride;
     const float *camP = (const float *)(ws + L.off_camP) + (int64_t)b * L.NB * L.RBH * L.cam_pitch;
     const int img = BL.Hp * BL.Wp;                                          // T1: [B][n_chunks][2][2][Hp][Wp]
-    const float *T1 = (const float *)(ws + BL.off_T1) + (int64_t)b * L.n_chunks * 4 * img;
+    const float *T1 = (const float *)(ws + BL.off_T1) + (int64_t)b * n_chunks * 4 * img;
     const uint8_t *tileany = (const uint8_t *)(ws + L.off_tileany) + (int64_t)b * L.NB * L.n_wtiles;
     // first band / column tile that can hold a cell of this block (the only divisions of the kernel)
     const int nb_lo = max(y0 - back, 0) / L.RB, wt_lo = max(x0 - back, 0) / L.WTC;
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
         if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
             const int at = h * L.cs_pitch + w;
             float am = 0.f, bs = 0.f;
-            for (int ch = 0; ch < L.n_chunks; ++ch) {
+            for (int ch = 0; ch < n_chunks; ++ch) {
                 am += Am[at + ch * chunk_stride];
                 bs += Bs[at + ch * chunk_stride];
             }
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
                     const int wt = wtA - dw;
                     if (dw ? !two_x : !hasA) continue;
                     const float *src = T1 + ((nb & 1) * 2 + (wt & 1)) * img + off;
-                    for (int ch = 0; ch < L.n_chunks; ++ch) acc += src[ch * 4 * img];
+                    for (int ch = 0; ch < n_chunks; ++ch) acc += src[ch * 4 * img];
                 }
             }
         }
@@ -610,6 +614,18 @@ __global__ void __launch_bounds__(kFinTX * kFinTY)
             }
         }
         camera_grad[((int64_t)b * p.H + y) * p.W + x] = acc;
+    }
+}
+
+static void launch_finalize(const Problem &p, const SlidingLayout &L, const BwdLayout &BL, const char *ws, float *camera_grad,
+                            uint32_t thr, dim3 fgrid, dim3 fblock, cudaStream_t stream) {
+    const bool one = L.n_chunks == 1;
+    if (p.k == 3) {
+        if (one) sliding_backward_finalize_kernel<3, true><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+        else sliding_backward_finalize_kernel<3, false><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    } else {
+        if (one) sliding_backward_finalize_kernel<5, true><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+        else sliding_backward_finalize_kernel<5, false><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
     }
 }
 
@@ -681,8 +697,7 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, grad, HeadGrad(), cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
     const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinRows - 1) / kFinRows, p.B), fblock(kFinTX, kFinTY);
-    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
-    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    launch_finalize(p, L, BL, ws, camera_grad, thr, fgrid, fblock, stream);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     if (thr != 0xffffffffu)
         return launch_tc_backward(p, grad, cam, proj, camera_grad, tc_scratch, (const uint32_t *)(ws + L.off_fb_count), thr, stream);
@@ -740,8 +755,7 @@ int launch_sliding_backward_head(const Problem &p, const float *soft_grad, const
     if (rc) return rc;
     if ((rc = launch_fallback_patch_grad(p, L, nullptr, hg, cam, proj, ws, (float *)(ws + BL.off_patch), thr, stream))) return rc;
     const dim3 fgrid((p.W + kFinTX - 1) / kFinTX, (p.H + kFinRows - 1) / kFinRows, p.B), fblock(kFinTX, kFinTY);
-    if (p.k == 3) sliding_backward_finalize_kernel<3><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
-    else sliding_backward_finalize_kernel<5><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+    launch_finalize(p, L, BL, ws, camera_grad, thr, fgrid, fblock, stream);
     CUSTMA_LAUNCH_CHECK("sliding_backward_finalize_kernel");
     return CUSTMA_OK;
 }
