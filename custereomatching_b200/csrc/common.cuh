@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "custma_b200.h"
 
 namespace custma {
@@ -79,6 +81,28 @@ void note_launch();
     } while (0)
 
 inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// Programmatic dependent launch (sm_90+): the kernels of one call form a chain of small dependent launches (prep,
+// main, fallback, decode / finalize).  A chained kernel starts with pdl_wait() - it returns once the preceding kernel of
+// the stream has completed and its writes are visible - and then pdl_release(), which lets the NEXT chained launch be
+// scheduled while this one is still running (its blocks wait in their own pdl_wait()).  Only the launch latency between
+// dependent kernels overlaps; ordering and visibility are those of plain stream order (every kernel waits before it
+// reads anything).  Both instructions are no-ops for a kernel launched the ordinary way.  CUSTMA_NO_PDL=1 switches the
+// launch attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- launchers implemented in the .cu files -------------------------------------------------------------------
 // per-pixel window statistics of one [B,H,W] image in the reference's own arithmetic order

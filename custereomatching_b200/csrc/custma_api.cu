@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sliding_common.cuh"
@@ -14,6 +15,11 @@ static thread_local char g_error[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = getenv("CUSTMA_NO_PDL") == nullptr;
+    return on;
+}
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;

@@ -405,6 +405,8 @@ template <int K, int NU, int WG, bool HG>
 __global__ void __launch_bounds__(16 * NU * WG, 1)
     sliding_backward_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL, char *__restrict__ ws,
                             const float *__restrict__ grad, const uint32_t tc_threshold, const HeadGrad hg) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     using F = SlideGeom<K, NU, WG>;
     constexpr int WTC = F::WTC, SC = F::SC, NS = F::NS, NCW = F::NCW;
     extern __shared__ __align__(128) float smem[];
@@ -486,6 +488,8 @@ template <int K, bool ONE>
 __global__ void __launch_bounds__(kFinTX * kFinTY)
     sliding_backward_finalize_kernel(const Problem p, const SlidingLayout L, const BwdLayout BL,
                                      const char *__restrict__ ws, float *__restrict__ camera_grad, const uint32_t tc_threshold) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     if (*reinterpret_cast<const uint32_t *>(ws + L.off_fb_count) > tc_threshold) return;
     const int n_chunks = ONE ? 1 : L.n_chunks;
     constexpr int r = K / 2, back = K - 1 - r, SW = kFinTX + K - 1, SH = kFinRows + K - 1;
@@ -621,11 +625,11 @@ static void launch_finalize(const Problem &p, const SlidingLayout &L, const BwdL
                             uint32_t thr, dim3 fgrid, dim3 fblock, cudaStream_t stream) {
     const bool one = L.n_chunks == 1;
     if (p.k == 3) {
-        if (one) sliding_backward_finalize_kernel<3, true><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
-        else sliding_backward_finalize_kernel<3, false><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+        if (one) launch_chained(sliding_backward_finalize_kernel<3, true>, fgrid, fblock, 0, stream, p, L, BL, ws, camera_grad, thr);
+        else launch_chained(sliding_backward_finalize_kernel<3, false>, fgrid, fblock, 0, stream, p, L, BL, ws, camera_grad, thr);
     } else {
-        if (one) sliding_backward_finalize_kernel<5, true><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
-        else sliding_backward_finalize_kernel<5, false><<<fgrid, fblock, 0, stream>>>(p, L, BL, ws, camera_grad, thr);
+        if (one) launch_chained(sliding_backward_finalize_kernel<5, true>, fgrid, fblock, 0, stream, p, L, BL, ws, camera_grad, thr);
+        else launch_chained(sliding_backward_finalize_kernel<5, false>, fgrid, fblock, 0, stream, p, L, BL, ws, camera_grad, thr);
     }
 }
 
@@ -636,7 +640,7 @@ static int launch_bwd_cfg(const Problem &p, const SlidingLayout &L, const BwdLay
     const size_t smem = BwdGeom<K, NU, WG>::SMEM_BYTES;
     auto kern = hg.state ? sliding_backward_kernel<K, NU, WG, true> : sliding_backward_kernel<K, NU, WG, false>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 16 * NU * WG, smem, stream>>>(p, L, BL, ws, grad, thr, hg);
+    CUSTMA_CUDA_CHECK(launch_chained(kern, grid, dim3(16 * NU * WG), smem, stream, p, L, BL, ws, grad, thr, hg));
     CUSTMA_LAUNCH_CHECK("sliding_backward_kernel");
     return CUSTMA_OK;
 }
@@ -710,6 +714,8 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
 __global__ void __launch_bounds__(256)
     head_grad_prep_kernel(int64_t pixels, const float4 *__restrict__ state, const float *__restrict__ soft_grad, float beta,
                           float4 *__restrict__ out) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= pixels) return;
     const float4 st = state[pix];                      // (beta_log2e * M, 1 / Z, soft, mask)

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256)
     fallback_proj_stats_kernel(const Problem p, const SlidingLayout L, const float *__restrict__ proj,
                                const uint32_t *__restrict__ bandany, float *__restrict__ pm_out,
                                float *__restrict__ ey2_out) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int nb = blockIdx.y, b = blockIdx.z;
     if (!bandany[b * L.NB + nb]) return;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                             const float *__restrict__ fb_pm, const float *__restrict__ fb_ey2,
                             float *__restrict__ cost, unsigned long long *__restrict__ keys, const uint32_t tc_threshold,
                             const HeadOut head) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     extern __shared__ float smem[];
     const uint32_t n_items = *fb_count;
     if (n_items > tc_threshold) return;   // so much is flagged that the tensor-core kernel computes the whole call
@@ -180,6 +184,8 @@ __global__ void __launch_bounds__(kFbWarps * 32)
                                const uint8_t *__restrict__ flags, const uint32_t *__restrict__ fb_count,
                                const uint32_t *__restrict__ fb_list, const float *__restrict__ fb_pm,
                                const float *__restrict__ fb_ey2, float *__restrict__ patch_grad, const uint32_t tc_threshold) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     extern __shared__ float smem[];
     const uint32_t n_items = *fb_count;
     if (n_items > tc_threshold) return;   // the tensor-core kernel computes the whole call
@@ -250,9 +256,9 @@ __global__ void __launch_bounds__(kFbWarps * 32)
 static int launch_fallback_proj_stats(const Problem &p, const SlidingLayout &L, const float *proj, const char *ws,
                                       cudaStream_t stream) {
     dim3 grid((p.W + 255) / 256, L.NB, p.B);
-    fallback_proj_stats_kernel<<<grid, 256, 0, stream>>>(p, L, proj, (const uint32_t *)(ws + L.off_bandany),
-                                                         (float *)(const_cast<char *>(ws) + L.off_fb_pm),
-                                                         (float *)(const_cast<char *>(ws) + L.off_fb_ey2));
+    CUSTMA_CUDA_CHECK(launch_chained(fallback_proj_stats_kernel, grid, dim3(256), 0, stream, p, L, proj,
+                                     (const uint32_t *)(ws + L.off_bandany), (float *)(const_cast<char *>(ws) + L.off_fb_pm),
+                                     (float *)(const_cast<char *>(ws) + L.off_fb_ey2)));
     CUSTMA_LAUNCH_CHECK("fallback_proj_stats_kernel");
     return CUSTMA_OK;
 }
@@ -267,10 +273,10 @@ int launch_fallback_forward(const Problem &p, const SlidingLayout &L, const floa
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "fallback forward: last axis %d too long for shared memory", p.C);
     if (smem > 48 * 1024)
         CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(fallback_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fallback_forward_kernel<<<fb_grid(), kFbWarps * 32, smem, stream>>>(
-        p, L, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
-        (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2), cost,
-        keys, tc_threshold, head);
+    CUSTMA_CUDA_CHECK(launch_chained(fallback_forward_kernel, dim3(fb_grid()), dim3(kFbWarps * 32), smem, stream, p, L, cam, proj,
+                                     (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
+                                     (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm),
+                                     (const float *)(ws + L.off_fb_ey2), cost, keys, tc_threshold, head));
     CUSTMA_LAUNCH_CHECK("fallback_forward_kernel");
     return CUSTMA_OK;
 }
@@ -287,10 +293,10 @@ int launch_fallback_patch_grad(const Problem &p, const SlidingLayout &L, const f
                                            (int)std::max<size_t>(smem, 48 * 1024)));
     int rc = launch_fallback_proj_stats(p, L, proj, ws, stream);
     if (rc) return rc;
-    fallback_patch_grad_kernel<<<fb_grid(), kFbWarps * 32, smem, stream>>>(
-        p, L, grad, hg, cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
-        (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm), (const float *)(ws + L.off_fb_ey2),
-        patch_grad, tc_threshold);
+    CUSTMA_CUDA_CHECK(launch_chained(fallback_patch_grad_kernel, dim3(fb_grid()), dim3(kFbWarps * 32), smem, stream, p, L, grad, hg,
+                                     cam, proj, (const uint8_t *)(ws + L.off_flags), (const uint32_t *)(ws + L.off_fb_count),
+                                     (const uint32_t *)(ws + L.off_fb_list), (const float *)(ws + L.off_fb_pm),
+                                     (const float *)(ws + L.off_fb_ey2), patch_grad, tc_threshold));
     CUSTMA_LAUNCH_CHECK("fallback_patch_grad_kernel");
     return CUSTMA_OK;
 }

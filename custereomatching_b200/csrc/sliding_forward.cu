@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(16 * NU * WG, 2)
     sliding_forward_kernel(const Problem p, const SlidingLayout L, const char *__restrict__ ws,
                            float *__restrict__ cost, unsigned long long *__restrict__ wta_keys, const uint32_t tc_threshold,
                            const HeadOut head) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     using G = SlideGeom<K, NU, WG>;
     constexpr int WTC = G::WTC, SC = G::SC, NS = G::NS, NCW = G::NCW;
     extern __shared__ __align__(128) float smem[];
@@ -261,6 +263,8 @@ __device__ __forceinline__ void forward_consumer(const Problem &p, float *smem, 
 __global__ void __launch_bounds__(256)
     wta_decode_kernel(Problem p, const unsigned long long *__restrict__ keys, float *__restrict__ best,
                       int32_t *__restrict__ index, const WtaExtras ex) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p.pixels()) return;
     const unsigned long long key = keys[pix];
@@ -292,6 +296,8 @@ __global__ void __launch_bounds__(256)
     head_decode_kernel(Problem p, const unsigned long long *__restrict__ keys, const HeadOut head,
                        float *__restrict__ soft, float *__restrict__ best, int32_t *__restrict__ index,
                        float *__restrict__ mask, float4 *__restrict__ state, float threshold) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p.pixels()) return;
     float M = -INFINITY;
@@ -333,7 +339,7 @@ static int launch_one(const Problem &p, const SlidingLayout &L, const char *ws, 
     auto kern = sliding_forward_kernel<K, NU, WG, COST, WTA, HEAD>;
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.n_wtiles * L.n_chunks, L.NB, p.B);
-    kern<<<grid, threads, smem, stream>>>(p, L, ws, cost, keys, tc_threshold, head);
+    CUSTMA_CUDA_CHECK(launch_chained(kern, grid, dim3(threads), smem, stream, p, L, ws, cost, keys, tc_threshold, head));
     CUSTMA_LAUNCH_CHECK("sliding_forward_kernel");
     return CUSTMA_OK;
 }
@@ -406,7 +412,8 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
             return rc;
     }
     if (best) {
-        wta_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, best, index, extras);
+        CUSTMA_CUDA_CHECK(launch_chained(wta_decode_kernel, dim3((unsigned)((p.pixels() + 255) / 256)), dim3(256), 0, stream, p,
+                                         (const unsigned long long *)keys, best, index, extras));
         CUSTMA_LAUNCH_CHECK("wta_decode_kernel");
     }
     return CUSTMA_OK;
@@ -452,8 +459,9 @@ int launch_sliding_forward_head(const Problem &p, const float *cam, const float 
                   : launch_k<7>(cfg, p, L, ws, nullptr, keys, thr, head, stream);
     if (rc) return rc;
     if ((rc = launch_fallback_forward(p, L, cam, proj, ws, nullptr, keys, head, thr, stream))) return rc;
-    head_decode_kernel<<<(unsigned)((p.pixels() + 255) / 256), 256, 0, stream>>>(p, keys, head, soft_disparity, best, index,
-                                                                                 mask, head_state, threshold);
+    CUSTMA_CUDA_CHECK(launch_chained(head_decode_kernel, dim3((unsigned)((p.pixels() + 255) / 256)), dim3(256), 0, stream, p,
+                                     (const unsigned long long *)keys, head, soft_disparity, best, index, mask, head_state,
+                                     threshold));
     CUSTMA_LAUNCH_CHECK("head_decode_kernel");
     return CUSTMA_OK;
 }

@@ -167,6 +167,8 @@ constexpr int kPivotThreads = 256;
 __global__ void __launch_bounds__(kPivotThreads)
     pivot_kernel(Problem p, SlidingLayout L, int tiles_per_block, const float *__restrict__ cam,
                  const float *__restrict__ proj, float *__restrict__ campiv, uint32_t *__restrict__ minmax) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     __shared__ float cmax[kPivotThreads], cmin[kPivotThreads];
     const bool is_proj = (int)blockIdx.z >= p.B;        // z >= B: the projector's band extrema (one pivot per band)
     const int nb = blockIdx.y, b = blockIdx.z % p.B, wt0 = blockIdx.x * tiles_per_block;
@@ -233,6 +235,8 @@ __global__ void __launch_bounds__(256)
     band_copy_kernel(Problem p, SlidingLayout L, const float *__restrict__ cam, const float *__restrict__ proj,
                      const uint32_t *__restrict__ minmax, const float *__restrict__ campiv,
                      float *__restrict__ camP, float *__restrict__ projP) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B;
     const int pitch = img ? L.proj_pitch : L.cam_pitch, left = L.proj_lp;
     const int t = blockIdx.y % L.RBH, nb = blockIdx.y / L.RBH;
@@ -274,6 +278,8 @@ __global__ void __launch_bounds__(128)
     band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ camP, const float *__restrict__ projP,
                       float *__restrict__ A, float *__restrict__ ex2, float *__restrict__ Sp,
                       float *__restrict__ ey2, float *__restrict__ rho_c, float *__restrict__ rho_p) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     // blockIdx.y = band * segments + segment: a thread marches kStatRows output rows (+ k-1 warm-up rows) of one column
     const int nseg = (L.RB + kStatRows - 1) / kStatRows;
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y / nseg, seg = blockIdx.y % nseg;
@@ -361,6 +367,8 @@ __global__ void __launch_bounds__(128)
     tile_flags_kernel(Problem p, SlidingLayout L, const float *__restrict__ rho_c, const float *__restrict__ rho_p,
                       uint8_t *__restrict__ flags, uint8_t *__restrict__ tileany, uint32_t *__restrict__ bandany,
                       uint32_t *__restrict__ fb_count, uint32_t *__restrict__ fb_list) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
     if (id >= ntiles) return;
@@ -400,21 +408,24 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
     }
     {
         dim3 grid((std::max(L.cam_pitch, L.proj_pitch) / 4 + 255) / 256, L.NB * L.RBH, 2 * p.B);
-        band_copy_kernel<<<grid, 256, 0, stream>>>(p, L, cam, proj, minmax, campiv, camP, projP);
+        CUSTMA_CUDA_CHECK(launch_chained(band_copy_kernel, grid, dim3(256), 0, stream, p, L, cam, proj, (const uint32_t *)minmax,
+                                         (const float *)campiv, camP, projP));
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
         dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB * ((L.RB + kStatRows - 1) / kStatRows), 2 * p.B);
         auto kern = p.k == 3 ? band_stats_kernel<3> : p.k == 5 ? band_stats_kernel<5> : band_stats_kernel<7>;
-        kern<<<grid, 128, 0, stream>>>(p, L, camP, projP, (float *)(ws + L.off_A), (float *)(ws + L.off_ex2),
-                                       (float *)(ws + L.off_Sp), (float *)(ws + L.off_ey2), rho_c, rho_p);
+        CUSTMA_CUDA_CHECK(launch_chained(kern, grid, dim3(128), 0, stream, p, L, (const float *)camP, (const float *)projP,
+                                         (float *)(ws + L.off_A), (float *)(ws + L.off_ex2), (float *)(ws + L.off_Sp),
+                                         (float *)(ws + L.off_ey2), rho_c, rho_p));
         CUSTMA_LAUNCH_CHECK("band_stats_kernel");
     }
     {
         const int64_t ntiles = (int64_t)p.B * L.NB * L.n_wtiles;
-        tile_flags_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, stream>>>(
-            p, L, rho_c, rho_p, (uint8_t *)(ws + L.off_flags), (uint8_t *)(ws + L.off_tileany),
-            (uint32_t *)(ws + L.off_bandany), (uint32_t *)(ws + L.off_fb_count), (uint32_t *)(ws + L.off_fb_list));
+        CUSTMA_CUDA_CHECK(launch_chained(tile_flags_kernel, dim3((unsigned)((ntiles + 127) / 128)), dim3(128), 0, stream, p, L,
+                                         (const float *)rho_c, (const float *)rho_p, (uint8_t *)(ws + L.off_flags),
+                                         (uint8_t *)(ws + L.off_tileany), (uint32_t *)(ws + L.off_bandany),
+                                         (uint32_t *)(ws + L.off_fb_count), (uint32_t *)(ws + L.off_fb_list)));
         CUSTMA_LAUNCH_CHECK("tile_flags_kernel");
     }
     return CUSTMA_OK;

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc_backward_kernel(const Problem p, const int RB, const int n_bands, const uint32_t *__restrict__ fb_count, const uint32_t threshold,
                        const float *__restrict__ cam_all, const float *__restrict__ proj_all, const float *__restrict__ grad,
                        float *__restrict__ scratch) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     using G = Geom<KW>;
     constexpr int R = G::R, NTAP = G::NTAP, TAPS = G::TAPS;
     // adaptive use: only when the sliding path's verdict flagged more work items than the threshold
@@ -440,6 +442,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 __global__ void __launch_bounds__(256)
     tc_backward_finalize_kernel(const Problem p, const int R, const int RB, const int n_bands, const uint32_t *__restrict__ fb_count,
                                 const uint32_t threshold, const float *__restrict__ scratch, float *__restrict__ out) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     if (fb_count != nullptr && *fb_count <= threshold) return;
     const int H = p.H, W = p.W;
     const int n_xt = (W + MT - 1) / MT;
@@ -487,9 +491,11 @@ static int launch_k(const Problem &p, const float *grad, const float *cam, const
     auto kern = tc_backward_kernel<KW>;
     const size_t smem = sizeof(Smem<KW>);
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)std::min<int64_t>(n_tiles, n_sm), NTHREADS, smem, stream>>>(p, RB, n_bands, fb_count, threshold, cam, proj, grad, scratch);
+    CUSTMA_CUDA_CHECK(launch_chained(kern, dim3((unsigned)std::min<int64_t>(n_tiles, n_sm)), dim3(NTHREADS), smem, stream, p, RB, n_bands,
+                                     fb_count, threshold, cam, proj, grad, scratch));
     CUSTMA_LAUNCH_CHECK("tc_backward_kernel");
-    tc_backward_finalize_kernel<<<(unsigned)std::min<int64_t>((p.pixels() + 255) / 256, 8 * n_sm), 256, 0, stream>>>(p, KW / 2, RB, n_bands, fb_count, threshold, scratch, camera_grad);
+    CUSTMA_CUDA_CHECK(launch_chained(tc_backward_finalize_kernel, dim3((unsigned)std::min<int64_t>((p.pixels() + 255) / 256, 8 * n_sm)), dim3(256), 0,
+                                     stream, p, KW / 2, RB, n_bands, fb_count, threshold, (const float *)scratch, camera_grad));
     CUSTMA_LAUNCH_CHECK("tc_backward_finalize_kernel");
     return CUSTMA_OK;
 }

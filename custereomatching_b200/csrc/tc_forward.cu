@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc_forward_kernel(const Problem p, const int RB, const int n_bands, const uint32_t *__restrict__ fb_count,
                       const uint32_t threshold, const float *__restrict__ cam_all, const float *__restrict__ proj_all,
                       float *__restrict__ cost, unsigned long long *__restrict__ keys) {
+    pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
+    pdl_release();
     using G = Geom<KW>;
     // adaptive use: only when the sliding path's verdict flagged more work items than the threshold
     if (fb_count != nullptr && *fb_count <= threshold) return;
@@ -379,7 +381,8 @@ static int launch_one(const Problem &p, const float *cam, const float *proj, flo
     auto kern = tc_forward_kernel<KW, COST, WTA>;
     const size_t smem = sizeof(Smem<KW>);
     CUSTMA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)std::min<int64_t>(n_tiles, n_sm), NTHREADS, smem, stream>>>(p, RB, n_bands, fb_count, threshold, cam, proj, cost, keys);
+    CUSTMA_CUDA_CHECK(launch_chained(kern, dim3((unsigned)std::min<int64_t>(n_tiles, n_sm)), dim3(NTHREADS), smem, stream, p, RB, n_bands,
+                                     fb_count, threshold, cam, proj, cost, keys));
     CUSTMA_LAUNCH_CHECK("tc_forward_kernel");
     return CUSTMA_OK;
 }
