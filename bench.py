@@ -640,7 +640,7 @@ def bench_batch(args, rank, local, world, device):
 
         for i in range(3):
             binding.host_wait(host_submit(i))
-        Ke = max(3, min(K, 20))
+        Ke = max(3, K)
         barrier()
         t0 = time.perf_counter()
         prev = None

@@ -1,9 +1,13 @@
 // custma_host_step: the host-buffer entry point (include/custma_b200.h).  Images come from host memory, results go
-// back to host memory; the batch is cut into chunks of pairs that are pipelined over two streams so that the
-// host->device copy of chunk i+1 and the device->host copy of chunk i-1 overlap the kernels of chunk i.
-// The cost volume stays in HBM.
+// back to host memory; the batch is cut into chunks of pairs that are pipelined so that the host->device copy of
+// chunk i+1 and the device->host copy of chunk i-1 overlap the kernels of chunk i: one stream for the copies in, one
+// for all kernels, one for the copies out, two sets of device buffers ("slots").  The cost volume stays in HBM.
+// (Round 1 gave every slot its own kernel stream; the kernels of two steps then shared the SMs whenever both were
+// ready, and a streamed step of 8 KITTI pairs took 2.74 ms instead of 2.47 ms - the device-resident step is 2.45 ms.
+// CUSTMA_HOST_PIPELINE=slots still selects that shape.)
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -13,10 +17,12 @@ namespace custma {
 constexpr int kSlots = 2;
 constexpr int kTickets = 8;   // completion events kept for custma_host_wait
 constexpr size_t kChunkVolumeBytes = (size_t)3 << 30;  // per-slot cost-volume chunk kept in HBM
+constexpr size_t kSingleStreamCells = (size_t)256 << 20;   // chunks of at least this many cells get the compute stream to themselves
 
 struct Slot {
-    cudaStream_t stream = nullptr, d2h = nullptr;   // kernels + host->device copies | device->host copies
+    cudaStream_t stream = nullptr, d2h = nullptr;   // kernels (+ host->device copies in the per-slot pipeline) | device->host copies
     cudaEvent_t fwd_done = nullptr, bwd_done = nullptr, d2h_done = nullptr;
+    cudaEvent_t h2d_done = nullptr, kernels_done = nullptr;   // single-compute-stream pipeline: inputs on the device | inputs free again
     float *cam = nullptr, *proj = nullptr, *best = nullptr, *grad = nullptr, *vol = nullptr;
     int32_t *index = nullptr;
     void *ws = nullptr;
@@ -32,6 +38,11 @@ struct HostCtx {
     uint32_t flags = 0;
     bool with_volume = false;
     Slot slot[kSlots];
+    // pipeline shape: one compute stream for every chunk (kernels of different chunks never share the SMs) fed by a
+    // host->device stream and drained by a device->host stream, or (CUSTMA_HOST_PIPELINE=slots) kernels and
+    // host->device copies of a chunk on its slot's own stream
+    bool single = true;
+    cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
     int next_slot = 0;                                 // slots keep rotating across calls, so consecutive steps overlap
     uint64_t next_ticket = 1;
     cudaEvent_t done[kTickets][kSlots] = {};           // done[t % kTickets][s]: slot s has delivered everything of ticket t
@@ -56,10 +67,14 @@ static void release_locked(HostCtx &g_ctx) {
         if (s.fwd_done) cudaEventDestroy(s.fwd_done);
         if (s.bwd_done) cudaEventDestroy(s.bwd_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.kernels_done) cudaEventDestroy(s.kernels_done);
         cudaFree(s.cam); cudaFree(s.proj); cudaFree(s.best); cudaFree(s.grad); cudaFree(s.vol); cudaFree(s.index);
         cudaFree(s.ws); cudaFree(s.u8);
         s = Slot();
     }
+    for (cudaStream_t st : {g_ctx.compute, g_ctx.h2d, g_ctx.d2h})
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto &row : g_ctx.done)
         for (cudaEvent_t &e : row)
             if (e) cudaEventDestroy(e);
@@ -93,9 +108,26 @@ static int build_ctx(HostCtx &g_ctx, int32_t chunk, int32_t H, int32_t W, int32_
     g_ctx.live = true; g_ctx.device = dev; g_ctx.H = H; g_ctx.W = W; g_ctx.D = D; g_ctx.k = k; g_ctx.flags = flags;
     g_ctx.chunk = chunk; g_ctx.with_volume = need_volume;
     const size_t img = (size_t)chunk * H * W * sizeof(float);
+    const char *shape = getenv("CUSTMA_HOST_PIPELINE");
+    // a chunk that fills the device runs alone; small chunks (one KITTI pair is 89 Mcell) gain more from sharing the SMs
+    // with the next step's kernels than they lose (measured: 0.42 against 0.49 ms per step)
+    g_ctx.single = (size_t)chunk * H * W * C >= kSingleStreamCells;
+    if (shape && strcmp(shape, "slots") == 0) g_ctx.single = false;
+    if (shape && strcmp(shape, "single") == 0) g_ctx.single = true;
+    if (g_ctx.single) {
+        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.compute, cudaStreamNonBlocking));
+        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.h2d, cudaStreamNonBlocking));
+        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.d2h, cudaStreamNonBlocking));
+    }
     for (Slot &s : g_ctx.slot) {
-        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
+        if (g_ctx.single) {
+            s.stream = nullptr; s.d2h = nullptr;
+            CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+            CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming));
+        } else {
+            CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
+        }
         CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.fwd_done, cudaEventDisableTiming));
         CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.bwd_done, cudaEventDisableTiming));
         CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
@@ -198,49 +230,68 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
         Slot &s = g_ctx.slot[g_ctx.next_slot];
         const int32_t nb = std::min(chunk, B - b0);
         const size_t img_bytes = (size_t)nb * pix * sizeof(float);
-        // the slot's result buffers are free once the device->host copies of its previous chunk are done
-        CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(s.stream, s.d2h_done, 0));
+        // streams of this chunk: copies in | kernels | copies out
+        cudaStream_t sin = g_ctx.single ? g_ctx.h2d : s.stream, sk = g_ctx.single ? g_ctx.compute : s.stream,
+                     sout = g_ctx.single ? g_ctx.d2h : s.d2h;
+        if (g_ctx.single) {
+            // the slot's image buffers are free once the kernels of its previous chunk are done
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sin, s.kernels_done, 0));
+        } else {
+            // the slot's result buffers are free once the device->host copies of its previous chunk are done
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sk, s.d2h_done, 0));
+        }
+        uint8_t *dc = nullptr, *dp = nullptr;
         if (!img.u8) {
-            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.cam, (const float *)img.cam + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
-            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.proj, (const float *)img.proj + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.cam, (const float *)img.cam + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, sin));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(s.proj, (const float *)img.proj + (size_t)b0 * pix, img_bytes, cudaMemcpyHostToDevice, sin));
         } else {
             // 8-bit images cross PCIe as they are (a quarter of the bytes per channel) and become fp32 planes on the device
             const size_t cb = (size_t)nb * pix * img.cam_channels, pb = (size_t)nb * pix * img.proj_channels;
             const size_t need = align256(cb) + align256(pb);
             if (s.u8_bytes < need) {
-                CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                CUSTMA_CUDA_CHECK(cudaStreamSynchronize(sin));
+                CUSTMA_CUDA_CHECK(cudaStreamSynchronize(sk));
                 cudaFree(s.u8);
                 s.u8 = nullptr; s.u8_bytes = 0;
                 CUSTMA_CUDA_CHECK(cudaMalloc(&s.u8, need));
                 s.u8_bytes = need;
             }
-            uint8_t *dc = s.u8, *dp = s.u8 + align256(cb);
-            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dc, (const uint8_t *)img.cam + (size_t)b0 * pix * img.cam_channels, cb, cudaMemcpyHostToDevice, s.stream));
-            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dp, (const uint8_t *)img.proj + (size_t)b0 * pix * img.proj_channels, pb, cudaMemcpyHostToDevice, s.stream));
-            if ((rc = custma_ingest_u8(dc, s.cam, nb, H, W, img.cam_channels, img.cam_channel, img.scale, s.stream))) return rc;
-            if ((rc = custma_ingest_u8(dp, s.proj, nb, H, W, img.proj_channels, img.proj_channel, img.scale, s.stream))) return rc;
+            dc = s.u8; dp = s.u8 + align256(cb);
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dc, (const uint8_t *)img.cam + (size_t)b0 * pix * img.cam_channels, cb, cudaMemcpyHostToDevice, sin));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(dp, (const uint8_t *)img.proj + (size_t)b0 * pix * img.proj_channels, pb, cudaMemcpyHostToDevice, sin));
+        }
+        if (g_ctx.single) {
+            CUSTMA_CUDA_CHECK(cudaEventRecord(s.h2d_done, sin));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sk, s.h2d_done, 0));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sk, s.d2h_done, 0));   // result buffers of the slot's previous chunk have left
+        }
+        if (img.u8) {
+            if ((rc = custma_ingest_u8(dc, s.cam, nb, H, W, img.cam_channels, img.cam_channel, img.scale, sk))) return rc;
+            if ((rc = custma_ingest_u8(dp, s.proj, nb, H, W, img.proj_channels, img.proj_channel, img.scale, sk))) return rc;
         }
         float *vol = cost_volume_dev ? cost_volume_dev + (size_t)b0 * pix * C : s.vol;
-        rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags, s.ws, s.ws_bytes, s.stream);
+        rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags, s.ws, s.ws_bytes, sk);
         if (rc) return rc;
-        // results leave on the slot's copy stream, so the backward kernels do not queue behind the copies
-        CUSTMA_CUDA_CHECK(cudaEventRecord(s.fwd_done, s.stream));
-        CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(s.d2h, s.fwd_done, 0));
-        CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_best + (size_t)b0 * pix, s.best, img_bytes, cudaMemcpyDeviceToHost, s.d2h));
+        // results leave on a copy stream, so the backward kernels do not queue behind the copies
+        CUSTMA_CUDA_CHECK(cudaEventRecord(s.fwd_done, sk));
+        CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sout, s.fwd_done, 0));
+        CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_best + (size_t)b0 * pix, s.best, img_bytes, cudaMemcpyDeviceToHost, sout));
         CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_index + (size_t)b0 * pix, s.index, (size_t)nb * pix * sizeof(int32_t),
-                                          cudaMemcpyDeviceToHost, s.d2h));
+                                          cudaMemcpyDeviceToHost, sout));
         if (cost_volume_grad_dev) {
             rc = custma_backward(cost_volume_grad_dev + (size_t)b0 * pix * C, s.cam, s.proj, s.grad, nb, H, W, D, k,
-                                 flags, s.ws, s.ws_bytes, s.stream);
+                                 flags, s.ws, s.ws_bytes, sk);
             if (rc) return rc;
-            CUSTMA_CUDA_CHECK(cudaEventRecord(s.bwd_done, s.stream));
-            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(s.d2h, s.bwd_done, 0));
-            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_camera_grad + (size_t)b0 * pix, s.grad, img_bytes, cudaMemcpyDeviceToHost, s.d2h));
+            CUSTMA_CUDA_CHECK(cudaEventRecord(s.bwd_done, sk));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sout, s.bwd_done, 0));
+            CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_camera_grad + (size_t)b0 * pix, s.grad, img_bytes, cudaMemcpyDeviceToHost, sout));
         }
-        CUSTMA_CUDA_CHECK(cudaEventRecord(s.d2h_done, s.d2h));
+        if (g_ctx.single) CUSTMA_CUDA_CHECK(cudaEventRecord(s.kernels_done, sk));
+        CUSTMA_CUDA_CHECK(cudaEventRecord(s.d2h_done, sout));
     }
     const uint64_t t = g_ctx.next_ticket++;
-    for (int i = 0; i < kSlots; ++i) CUSTMA_CUDA_CHECK(cudaEventRecord(g_ctx.done[t % kTickets][i], g_ctx.slot[i].d2h));
+    for (int i = 0; i < kSlots; ++i)
+        CUSTMA_CUDA_CHECK(cudaEventRecord(g_ctx.done[t % kTickets][i], g_ctx.single ? g_ctx.d2h : g_ctx.slot[i].d2h));
     if (ticket) *ticket = ((uint64_t)(ci + 1) << 56) | t;
     return CUSTMA_OK;
 }
@@ -286,9 +337,11 @@ int custma_host_wait(uint64_t ticket) {
     for (HostCtx &c : g_ctxs) {
         if (!c.live) continue;
         for (Slot &s : c.slot) {
-            CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-            CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
+            if (s.stream) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+            if (s.d2h) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
         }
+        for (cudaStream_t st : {c.h2d, c.compute, c.d2h})
+            if (st) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(st));
     }
     return CUSTMA_OK;
 }
