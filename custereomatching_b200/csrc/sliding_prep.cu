@@ -87,7 +87,7 @@ void make_sliding_layout(const Problem &p, const SlidingConfig &cfg, bool backwa
             if (cost(rb) * 100 <= best * 112) { RB = rb; break; }
         }
     }
-    if (const char *e = getenv("CUSTMA_BANDS")) {   // experiment: force the number of bands
+    if (const char *e = getenv(backward ? "CUSTMA_BANDS_BWD" : "CUSTMA_BANDS")) {   // experiment: force the number of bands
         const int nb = atoi(e);
         if (nb > 0) RB = std::min(128, fit_up((p.H + nb - 1) / nb));
     }
