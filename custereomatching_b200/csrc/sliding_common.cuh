@@ -137,6 +137,43 @@ __device__ __forceinline__ float rsqrt_fast(float x) {  // MUFU.RSQ, 2 ulp; x >=
     return y;
 }
 
+// Packed fp32 pairs.  sm_100 issues two IEEE fp32 operations per FFMA2 / FADD2 / FMUL2 instruction; every half rounds
+// exactly like the scalar instruction, so a packed formulation is bit-identical to the scalar one it replaces.  An
+// operand is an aligned 64-bit register pair in either order (the instruction can swap its halves) or one 32-bit
+// register broadcast to both halves: pk2(x, x) and pk2(hi, lo) of two neighbouring registers cost nothing, a pair that
+// straddles an alignment boundary costs a move.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // order-preserving map float -> uint32 (so that integer max is float max); never returns 0 for a finite float
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -211,6 +248,55 @@ struct BoxRing {
                 P[Q][i][j] = s + cprev[i][j];
                 cprev[i][j] = s;
                 bx[i][j] = box;
+            }
+        }
+    }
+};
+
+// BoxRing on packed pairs: pair jp of column i holds the disparities (2 jp, 2 jp + 1); the same operations in the same
+// order per cell, two cells per instruction
+template <int K>
+struct BoxRing2 {
+    f32x2 cprev[4][2];
+    f32x2 P[K - 2][4][2];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                cprev[i][jp] = 0ull;
+#pragma unroll
+                for (int m = 0; m < K - 2; ++m) P[m][i][jp] = 0ull;
+            }
+    }
+    template <int DIR>
+    __device__ __forceinline__ void step(const int Q, const float *c, const float *pj, float seed, f32x2 (&bx)[4][2]) {
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+            const int j = 2 * jp;
+            // the projector values of disparities (j, j + 1) at camera column n: pj[n + 3 - j], pj[n + 2 - j]
+            auto pp = [&](int n) { return pk2(pj[n + 3 - j], pj[n + 2 - j]); };
+            f32x2 s = 0ull;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int i = DIR == 2 ? 3 - n : n;
+                if (n == 0 || DIR == 0) {
+                    s = fma2(pk2(c[i], c[i]), pp(i), pk2(seed, seed));
+#pragma unroll
+                    for (int x = 1; x < K; ++x) s = fma2(pk2(c[i + x], c[i + x]), pp(i + x), s);
+                } else if (DIR == 1) {
+                    s = fma2(pk2(c[i + K - 1], c[i + K - 1]), pp(i + K - 1), s);
+                    s = fma2(pk2(-c[i - 1], -c[i - 1]), pp(i - 1), s);
+                } else {
+                    s = fma2(pk2(c[i], c[i]), pp(i), s);
+                    s = fma2(pk2(-c[i + K], -c[i + K]), pp(i + K), s);
+                }
+                f32x2 box = s;
+#pragma unroll
+                for (int m = 1; m <= K - 2; m += 2) box = add2(box, P[(Q - m + 2 * (K - 2)) % (K - 2)][i][jp]);
+                P[Q][i][jp] = add2(s, cprev[i][jp]);
+                cprev[i][jp] = s;
+                bx[i][jp] = box;
             }
         }
     }
