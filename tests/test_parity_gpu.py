@@ -4,6 +4,8 @@ against the golden vectors of the reference extension and against the CPU oracle
 Tolerances (conftest.py): costs |new-ref| <= 1e-5 * max(1,|ref|); gradients |new-ref| <= 1e-5 * max|ref grad|;
 WTA indices bit-exact wherever the best cost beats the runner-up by more than 1e-5 (BASELINE.json north_star).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -16,6 +18,7 @@ from oracle import ref_port
 from oracle import zncc_oracle as zo
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMALL = golden_small_names()
 FLAGS = [0, cb.FLAG_DIRECT]
 
@@ -270,6 +273,70 @@ def test_host_entry_points_keep_two_shapes_alive():
         assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp)
     binding.host_wait(0)
     binding.host_release()
+
+
+@pytest.mark.parametrize("shape", ["single", "slots"])
+def test_host_pipeline_shapes_agree_with_the_device_path(shape, monkeypatch):
+    """Both shapes of the host pipeline (one compute stream for every chunk | a kernel stream per buffer slot;
+    host_pipeline.cu picks by chunk size, CUSTMA_HOST_PIPELINE forces one) deliver the device path's bits, streamed
+    (three tickets in flight over two slots) and synchronous (custma_host_step cuts the batch into two chunks)."""
+    from custereomatching_b200 import binding
+    binding.host_release()
+    monkeypatch.setenv("CUSTMA_HOST_PIPELINE", shape)
+    B, H, W, D, k = 4, 36, 150, 32, 5
+    sets = []
+    for i in range(3):
+        cam, proj = rand_pair(H, W, seed=80 + i, B=B)
+        g = np.random.RandomState(90 + i).randn(B, H, W, D).astype(np.float32)
+        sets.append((torch.from_numpy(cam).pin_memory(), torch.from_numpy(proj).pin_memory(), dev(g),
+                     torch.empty(B, H, W).pin_memory(), torch.empty(B, H, W, dtype=torch.int32).pin_memory(),
+                     torch.empty(B, H, W).pin_memory()))
+    torch.cuda.synchronize()
+    tickets = [binding.host_submit(c.data_ptr(), p.data_ptr(), hb.data_ptr(), hi.data_ptr(), hg.data_ptr(), 0, g.data_ptr(),
+                                   B, H, W, D, k) for c, p, g, hb, hi, hg in sets]
+    binding.host_wait(tickets[-1])
+    binding.host_wait(0)
+    for c, p, g, hb, hi, hg in sets:
+        _, best, disp = cb.forward(c.cuda(), p.cuda(), D, k, want_cost=False, want_wta=True)
+        grad = cb.backward(g, c.cuda(), p.cuda(), k, D)
+        assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp) and torch.equal(hg.cuda(), grad)
+    # synchronous entry point on the same context
+    c, p, g, hb, hi, hg = sets[0]
+    hb.zero_(); hi.zero_(); hg.zero_()
+    binding.host_step(c.data_ptr(), p.data_ptr(), hb.data_ptr(), hi.data_ptr(), hg.data_ptr(), 0, g.data_ptr(), B, H, W, D, k)
+    _, best, disp = cb.forward(c.cuda(), p.cuda(), D, k, want_cost=False, want_wta=True)
+    assert torch.equal(hb.cuda(), best) and torch.equal(hi.cuda(), disp)
+    assert torch.equal(hg.cuda(), cb.backward(g, c.cuda(), p.cuda(), k, D))
+    binding.host_release()
+
+
+def test_plain_launches_give_the_same_bits_as_chained_launches():
+    """CUSTMA_NO_PDL=1 (read once per process) launches every kernel in plain stream order; programmatic dependent
+    launch only overlaps launch latencies, so forward, WTA and backward must not change by a bit."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, hashlib\n"
+        "from custereomatching_b200 import functional as cb\n"
+        "rng = np.random.RandomState(5)\n"
+        "cam = torch.from_numpy(rng.rand(2, 40, 170).astype(np.float32)).cuda()\n"
+        "proj = torch.from_numpy(rng.rand(2, 40, 170).astype(np.float32)).cuda()\n"
+        "g = torch.from_numpy(rng.randn(2, 40, 170, 64).astype(np.float32)).cuda()\n"
+        "cost, best, disp = cb.forward(cam, proj, 64, 5, want_cost=True, want_wta=True)\n"
+        "grad = cb.backward(g, cam, proj, 5, 64)\n"
+        "h = hashlib.sha256()\n"
+        "for t in (cost, best, disp, grad): h.update(t.cpu().numpy().tobytes())\n"
+        "print('DIGEST', h.hexdigest())\n")
+    digests = []
+    for no_pdl in (False, True):
+        env = dict(os.environ)
+        env.pop("CUSTMA_NO_PDL", None)
+        if no_pdl:
+            env["CUSTMA_NO_PDL"] = "1"
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
 
 
 def test_error_behaviour():
