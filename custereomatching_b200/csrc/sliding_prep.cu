@@ -299,19 +299,23 @@ __global__ void __launch_bounds__(256)
 // Conditioning of a window: rho = n * max|v|^2 / e2 (how much larger the raw sums are than what survives the
 // cancellation); the worst rho per block of 16 columns feeds the tile verdict.  rho = 0 for an exactly constant window
 // of pivoted zeros, infinite for any other flat window.
-constexpr int kStatRows = 24;   // output rows per thread of band_stats_kernel (+ k-1 warm-up rows)
+// Output rows per thread of band_stats_kernel (+ k-1 warm-up rows): 24, or 12 / 8 when a call is too small to fill the
+// device with 24 (one KITTI pair: 24 -> 11 us).  A thread's shift comes from the 24-row block its rows lie in, so the
+// statistics do not depend on the choice by a bit.
+constexpr int kStatRows = 24;
 
 template <int K>
 __global__ void __launch_bounds__(128)
     band_stats_kernel(Problem p, SlidingLayout L, const float *__restrict__ camP, const float *__restrict__ projP,
                       float *__restrict__ A, float *__restrict__ ex2, float *__restrict__ Sp,
-                      float *__restrict__ ey2, float *__restrict__ rho_c, float *__restrict__ rho_p) {
+                      float *__restrict__ ey2, float *__restrict__ rho_c, float *__restrict__ rho_p, const int stat_rows) {
     pdl_wait();      // chained launch (common.cuh): the preceding kernel is complete and visible from here on
     pdl_release();
-    // blockIdx.y = band * segments + segment: a thread marches kStatRows output rows (+ k-1 warm-up rows) of one column
-    const int nseg = (L.RB + kStatRows - 1) / kStatRows;
+    // blockIdx.y = band * segments + segment: a thread marches stat_rows output rows (+ k-1 warm-up rows) of one column
+    const int nseg = (L.RB + stat_rows - 1) / stat_rows;
     const int img = blockIdx.z / p.B, b = blockIdx.z % p.B, nb = blockIdx.y / nseg, seg = blockIdx.y % nseg;
-    const int t_begin = seg * kStatRows, t_end = min(L.RBH, t_begin + kStatRows + K - 1);
+    const int t_begin = seg * stat_rows, t_end = min(L.RBH, t_begin + stat_rows + K - 1);
+    const int t_shift = t_begin / kStatRows * kStatRows;   // stat_rows divides kStatRows: segments nest in 24-row blocks
     const int pitch = img ? L.ps_pitch : L.cs_pitch, left = img ? L.ps_ld : 0;
     const int pitchP = img ? L.proj_pitch : L.cam_pitch;
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(128)
     float r1[K - 1], r2[K - 1], rm[K - 1];
 #pragma unroll
     for (int m = 0; m < K - 1; ++m) r1[m] = r2[m] = rm[m] = 0.f;
-    const float shift = col_ok ? src[(int64_t)min(t_begin + K / 2, L.RBH - 1) * pitchP + K / 2] : 0.f;
+    const float shift = col_ok ? src[(int64_t)min(t_shift + K / 2, L.RBH - 1) * pitchP + K / 2] : 0.f;
     float rho = 0.f;
     for (int t = t_begin; t < t_end; ++t) {
         float h1 = 0.f, h2 = 0.f, hm = 0.f;
@@ -441,11 +445,16 @@ int launch_sliding_prep(const Problem &p, const SlidingLayout &L, const float *c
         CUSTMA_LAUNCH_CHECK("band_copy_kernel");
     }
     {
-        dim3 grid((std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, L.NB * ((L.RB + kStatRows - 1) / kStatRows), 2 * p.B);
+        // one wave of 128-thread blocks at 16 per SM
+        const int64_t xblocks = (std::max(L.cs_pitch, L.ps_pitch) + 127) / 128, wave = 16 * (int64_t)device_sm_count();
+        int stat_rows = kStatRows;
+        for (int r : {12, 8})
+            if (xblocks * L.NB * ((L.RB + stat_rows - 1) / stat_rows) * 2 * p.B < wave) stat_rows = r;
+        dim3 grid((unsigned)xblocks, L.NB * ((L.RB + stat_rows - 1) / stat_rows), 2 * p.B);
         auto kern = p.k == 3 ? band_stats_kernel<3> : p.k == 5 ? band_stats_kernel<5> : band_stats_kernel<7>;
         CUSTMA_CUDA_CHECK(launch_chained(kern, grid, dim3(128), 0, stream, p, L, (const float *)camP, (const float *)projP,
                                          (float *)(ws + L.off_A), (float *)(ws + L.off_ex2), (float *)(ws + L.off_Sp),
-                                         (float *)(ws + L.off_ey2), rho_c, rho_p));
+                                         (float *)(ws + L.off_ey2), rho_c, rho_p, stat_rows));
         CUSTMA_LAUNCH_CHECK("band_stats_kernel");
     }
     {
