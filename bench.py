@@ -478,9 +478,19 @@ def bench_batch(args, rank, local, world, device):
     ws_bytes = max(binding.forward_workspace_bytes(P, H, W, D, k, flags),
                    binding.backward_workspace_bytes(P, H, W, D, k, flags))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    # the backward's image-dependent preparation runs on a second stream beside the forward, into its own workspace
+    # (custma_backward_prepare / CUSTMA_FLAG_PREPARED; --no-prepare: the plain two calls)
+    prepare = not args.no_prepare
+    ws_bwd_bytes = binding.backward_workspace_bytes(P, H, W, D, k, flags)
+    ws_bwd = torch.empty(max(ws_bwd_bytes, 256), dtype=torch.uint8, device=device) if prepare else None
+    prep_stream = torch.cuda.Stream(device) if prepare else None
     gather_res = ResultGather((2, P, H, W), torch.float32, device, rank, world, args.gather)
     gather_grad = ResultGather((P, H, W), torch.float32, device, rank, world, args.gather)
-    stream = torch.cuda.current_stream(device)
+    # the step runs on a high-priority stream, so that the backward's preparation (prep_stream, default priority) only
+    # takes what the forward leaves idle
+    torch.cuda.synchronize(device)
+    stream = torch.cuda.Stream(device, priority=-1) if prepare else torch.cuda.current_stream(device)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
     def fwd():
@@ -491,18 +501,33 @@ def bench_batch(args, rank, local, world, device):
         binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), (cam_grad if out is None else out).data_ptr(),
                          P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sptr)
 
+    def prepare_bwd(main, side):
+        side.wait_stream(main)
+        binding.backward_prepare(cam.data_ptr(), proj.data_ptr(), P, H, W, D, k, flags, ws_bwd.data_ptr(), ws_bwd_bytes,
+                                 side.cuda_stream)
+
+    def bwd_prepared(out, main, side):
+        main.wait_stream(side)
+        binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), out.data_ptr(), P, H, W, D, k,
+                         flags | binding.FLAG_PREPARED, ws_bwd.data_ptr(), ws_bwd_bytes, main.cuda_stream)
+
     state = {"i": 0, "grad_pending": None}
 
     def step_eager():
         # results only cross GPUs: 3 * P*H*W*4 bytes per rank; the volume never leaves its GPU.  Both transfers are
         # asynchronous: best / disparity leave under this step's backward, the camera gradient under the NEXT step's
         # forward; finish_steps() waits for the last one inside the timed region.
+        if prepare:
+            prepare_bwd(stream, prep_stream)
         fwd()
         pending = gather_res.start(results, stream)
         gather_grad.wait(state["grad_pending"], stream)
         out = cam_grad2[state["i"] & 1]
         state["i"] += 1
-        bwd(out)
+        if prepare:
+            bwd_prepared(out, stream, prep_stream)
+        else:
+            bwd(out)
         state["grad_pending"] = gather_grad.start(out, stream)
         gather_res.wait(pending, stream)
 
@@ -531,10 +556,15 @@ def bench_batch(args, rank, local, world, device):
             sp = side.cuda_stream
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
+                if prepare:
+                    prepare_bwd(side, prep_stream)
                 binding.forward(cam.data_ptr(), proj.data_ptr(), cost.data_ptr(), best.data_ptr(), disp.data_ptr(),
                                 P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sp)
-                binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(),
-                                 P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sp)
+                if prepare:
+                    bwd_prepared(cam_grad, side, prep_stream)
+                else:
+                    binding.backward(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(),
+                                     P, H, W, D, k, flags, ws.data_ptr(), ws_bytes, sp)
         stream.wait_stream(side)
         step = graph.replay
         for _ in range(3):
@@ -691,6 +721,7 @@ def bench_batch(args, rank, local, world, device):
                    "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
                    "result_gather": gather_res.mode, "gathered_equals_local": gather_ok,
                    "cuda_graph": graph is not None,
+                   "backward_prepared_beside_forward": prepare,
                    "l2": f"inputs larger than L2: {4 * cells_rank / 1e6:.0f} MB volume written and "
                          f"{4 * cells_rank / 1e6:.0f} MB gradient read per step per GPU (L2 = 126 MB)",
                    "kernels": "direct two-pass" if args.direct else "default (sliding-window where available)",
@@ -846,6 +877,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="cfg5 only: a shorter image (quick runs)")
     ap.add_argument("--direct", action="store_true", help="force the direct two-pass kernels (CUSTMA_FLAG_DIRECT)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prepare", action="store_true",
+                    help="plain custma_forward + custma_backward (default: custma_backward_prepare beside the forward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-rows", type=int, default=48, help="image rows of one pair in the CPU sample")
     args = ap.parse_args()

@@ -10,7 +10,7 @@ The drop-in Python surface of the reference lives in the top-level `custma` pack
 """
 from . import binding
 from .functional import (FLAG_DIRECT, FLAG_TENSOR, INVALID_COST, backward, backward_projector, confidence_mask, cost_volume, cost_volume_and_wta,
-                         forward, ingest_u8, soft_disparity, wta, wta_masked)
+                         forward, ingest_u8, prepare_backward, soft_disparity, wta, wta_masked)
 
-__all__ = ["binding", "forward", "backward", "backward_projector", "cost_volume", "wta", "wta_masked", "cost_volume_and_wta", "confidence_mask",
+__all__ = ["binding", "forward", "backward", "prepare_backward", "backward_projector", "cost_volume", "wta", "wta_masked", "cost_volume_and_wta", "confidence_mask",
            "ingest_u8", "soft_disparity", "FLAG_DIRECT", "FLAG_TENSOR", "INVALID_COST"]

@@ -22,8 +22,9 @@ ERR_CUDA = 3
 ERR_UNSUPPORTED = 4
 FLAG_DIRECT = 1
 FLAG_TENSOR = 2
+FLAG_PREPARED = 4
 INVALID_COST = -2.0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/custma_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = (
@@ -38,6 +39,7 @@ SYMBOLS = (
     "custma_forward_wta",
     "custma_backward",
     "custma_backward_rows",
+    "custma_backward_prepare",
     "custma_ingest_u8",
     "custma_backward_projector_workspace_bytes",
     "custma_backward_projector",
@@ -84,6 +86,8 @@ def _declare(lib):
                                        _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward.restype = ctypes.c_int
     lib.custma_backward.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_backward_prepare.restype = ctypes.c_int
+    lib.custma_backward_prepare.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward_rows.restype = ctypes.c_int
     lib.custma_backward_rows.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _u32, _ptr,
                                          _size, _ptr]
@@ -185,6 +189,12 @@ def backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W,
     rc = load().custma_backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin,
                                      row_end, flags, ws_ptr or None, ws_bytes, stream or None)
     check(rc, "custma_backward_rows")
+
+
+def backward_prepare(camera_ptr, projector_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    """The image-dependent part of backward(), ahead of time; then backward(..., flags | FLAG_PREPARED) on the same workspace."""
+    rc = load().custma_backward_prepare(camera_ptr, projector_ptr, B, H, W, D, k, flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_backward_prepare")
 
 
 def backward_projector_workspace_bytes(B, H, W, D, k, flags=0) -> int:

@@ -133,6 +133,7 @@ size_t custma_forward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D
 }
 
 size_t custma_backward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    flags &= ~CUSTMA_FLAG_PREPARED;
     Problem p;
     if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
     return backward_ws(p, flags);
@@ -212,18 +213,22 @@ int custma_forward_wta(const float *camera, const float *projector, float *cost_
 
 static int backward_impl(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
                          int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, int32_t row_begin, int32_t row_end,
-                         uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+                         uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_, bool prepare_only = false) {
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);
     if (rc) return rc;
-    if (!cost_volume_grad || !camera || !projector || !camera_grad)
+    const BackwardPhase phase = prepare_only ? kBackwardPrepareOnly : (flags & CUSTMA_FLAG_PREPARED) ? kBackwardPrepared : kBackwardAll;
+    flags &= ~CUSTMA_FLAG_PREPARED;
+    if (prepare_only) {
+        if (!camera || !projector) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera and projector must not be NULL");
+    } else if (!cost_volume_grad || !camera || !projector || !camera_grad)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "cost_volume_grad, camera, projector and camera_grad must not be NULL");
     if (row_begin < 0 || row_end > H || row_begin >= row_end)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "gradient rows [%d, %d) must be a non-empty range inside [0, %d)", row_begin, row_end, H);
     p.g0 = row_begin; p.g1 = row_end;
-    if ((rc = check_volume_alignment(p, cost_volume_grad, "cost_volume_grad"))) return rc;
+    if (!prepare_only && (rc = check_volume_alignment(p, cost_volume_grad, "cost_volume_grad"))) return rc;
     if ((rc = check_image_alignment(camera, "camera")) || (rc = check_image_alignment(projector, "projector")) ||
-        (rc = check_image_alignment(camera_grad, "camera_grad")))
+        (!prepare_only && (rc = check_image_alignment(camera_grad, "camera_grad"))))
         return rc;
     if ((rc = check_device())) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -233,9 +238,12 @@ static int backward_impl(const float *cost_volume_grad, const float *camera, con
         return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 540, k = 3 or 5, and no CUSTMA_FLAG_DIRECT");
     if (use_sliding_bwd(p, flags))
         return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, s.rest, s.rest_bytes,
-                                       (flags & CUSTMA_FLAG_TENSOR) != 0, stream);
-    if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
-    if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+                                       (flags & CUSTMA_FLAG_TENSOR) != 0, stream, phase);
+    if (phase != kBackwardPrepared) {   // the direct kernels' preparation: window means and second moments of both images
+        if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
+        if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+    }
+    if (phase == kBackwardPrepareOnly) return CUSTMA_OK;
     return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,
                                   (float *)s.rest, camera_grad, stream);
 }
@@ -245,6 +253,12 @@ int custma_backward(const float *cost_volume_grad, const float *camera, const fl
                     size_t workspace_bytes, void *stream_) {
     return backward_impl(cost_volume_grad, camera, projector, camera_grad, B, H, W, D, k, 0, H, flags, workspace,
                          workspace_bytes, stream_);
+}
+
+int custma_backward_prepare(const float *camera, const float *projector, int32_t B, int32_t H, int32_t W, int32_t D,
+                            int32_t k, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    return backward_impl(nullptr, camera, projector, nullptr, B, H, W, D, k, 0, H, flags & ~CUSTMA_FLAG_PREPARED, workspace,
+                         workspace_bytes, stream_, true);
 }
 
 int custma_backward_rows(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,

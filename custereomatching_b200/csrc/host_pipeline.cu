@@ -23,6 +23,9 @@ struct Slot {
     cudaStream_t stream = nullptr, d2h = nullptr;   // kernels (+ host->device copies in the per-slot pipeline) | device->host copies
     cudaEvent_t fwd_done = nullptr, bwd_done = nullptr, d2h_done = nullptr;
     cudaEvent_t h2d_done = nullptr, kernels_done = nullptr;   // single-compute-stream pipeline: inputs on the device | inputs free again
+    cudaEvent_t prep_done = nullptr;   // the backward's image-dependent preparation (side stream, under the forward) is in ws_bwd
+    void *ws_bwd = nullptr;            // single-compute-stream pipeline: the backward's own workspace
+    size_t ws_bwd_bytes = 0;
     float *cam = nullptr, *proj = nullptr, *best = nullptr, *grad = nullptr, *vol = nullptr;
     int32_t *index = nullptr;
     void *ws = nullptr;
@@ -43,6 +46,7 @@ struct HostCtx {
     // host->device copies of a chunk on its slot's own stream
     bool single = true;
     cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t prep = nullptr;   // lowest priority: the next backward's preparation fills what the forward leaves idle
     int next_slot = 0;                                 // slots keep rotating across calls, so consecutive steps overlap
     uint64_t next_ticket = 1;
     cudaEvent_t done[kTickets][kSlots] = {};           // done[t % kTickets][s]: slot s has delivered everything of ticket t
@@ -69,11 +73,13 @@ static void release_locked(HostCtx &g_ctx) {
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernels_done) cudaEventDestroy(s.kernels_done);
+        if (s.prep_done) cudaEventDestroy(s.prep_done);
+        cudaFree(s.ws_bwd);
         cudaFree(s.cam); cudaFree(s.proj); cudaFree(s.best); cudaFree(s.grad); cudaFree(s.vol); cudaFree(s.index);
         cudaFree(s.ws); cudaFree(s.u8);
         s = Slot();
     }
-    for (cudaStream_t st : {g_ctx.compute, g_ctx.h2d, g_ctx.d2h})
+    for (cudaStream_t st : {g_ctx.compute, g_ctx.h2d, g_ctx.d2h, g_ctx.prep})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto &row : g_ctx.done)
         for (cudaEvent_t &e : row)
@@ -115,15 +121,24 @@ static int build_ctx(HostCtx &g_ctx, int32_t chunk, int32_t H, int32_t W, int32_
     if (shape && strcmp(shape, "slots") == 0) g_ctx.single = false;
     if (shape && strcmp(shape, "single") == 0) g_ctx.single = true;
     if (g_ctx.single) {
-        CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.compute, cudaStreamNonBlocking));
+        int prio_low = 0, prio_high = 0;
+        CUSTMA_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CUSTMA_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.compute, cudaStreamNonBlocking, prio_high));
         CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.h2d, cudaStreamNonBlocking));
         CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.d2h, cudaStreamNonBlocking));
+        if (!getenv("CUSTMA_HOST_NO_PREPARE"))
+            CUSTMA_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.prep, cudaStreamNonBlocking, prio_low));
     }
     for (Slot &s : g_ctx.slot) {
         if (g_ctx.single) {
             s.stream = nullptr; s.d2h = nullptr;
             CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
             CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming));
+            if (g_ctx.prep) {
+                CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.prep_done, cudaEventDisableTiming));
+                s.ws_bwd_bytes = custma_backward_workspace_bytes(chunk, H, W, D, k, flags);
+                CUSTMA_CUDA_CHECK(cudaMalloc(&s.ws_bwd, std::max<size_t>(s.ws_bwd_bytes, 256)));
+            }
         } else {
             CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CUSTMA_CUDA_CHECK(cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking));
@@ -269,6 +284,15 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
             if ((rc = custma_ingest_u8(dc, s.cam, nb, H, W, img.cam_channels, img.cam_channel, img.scale, sk))) return rc;
             if ((rc = custma_ingest_u8(dp, s.proj, nb, H, W, img.proj_channels, img.proj_channel, img.scale, sk))) return rc;
         }
+        // the backward's preparation needs the images only: it runs beside the forward on the lowest-priority stream
+        // (its blocks take what the forward's last wave leaves idle) into the backward's own workspace
+        const bool prepare = g_ctx.single && g_ctx.prep && cost_volume_grad_dev && !img.u8;
+        if (prepare) {
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(g_ctx.prep, s.h2d_done, 0));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(g_ctx.prep, s.kernels_done, 0));   // ws_bwd's previous user
+            if ((rc = custma_backward_prepare(s.cam, s.proj, nb, H, W, D, k, flags, s.ws_bwd, s.ws_bwd_bytes, g_ctx.prep))) return rc;
+            CUSTMA_CUDA_CHECK(cudaEventRecord(s.prep_done, g_ctx.prep));
+        }
         float *vol = cost_volume_dev ? cost_volume_dev + (size_t)b0 * pix * C : s.vol;
         rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags, s.ws, s.ws_bytes, sk);
         if (rc) return rc;
@@ -279,8 +303,14 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
         CUSTMA_CUDA_CHECK(cudaMemcpyAsync(h_index + (size_t)b0 * pix, s.index, (size_t)nb * pix * sizeof(int32_t),
                                           cudaMemcpyDeviceToHost, sout));
         if (cost_volume_grad_dev) {
-            rc = custma_backward(cost_volume_grad_dev + (size_t)b0 * pix * C, s.cam, s.proj, s.grad, nb, H, W, D, k,
-                                 flags, s.ws, s.ws_bytes, sk);
+            if (prepare) {
+                CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sk, s.prep_done, 0));
+                rc = custma_backward(cost_volume_grad_dev + (size_t)b0 * pix * C, s.cam, s.proj, s.grad, nb, H, W, D, k,
+                                     flags | CUSTMA_FLAG_PREPARED, s.ws_bwd, s.ws_bwd_bytes, sk);
+            } else {
+                rc = custma_backward(cost_volume_grad_dev + (size_t)b0 * pix * C, s.cam, s.proj, s.grad, nb, H, W, D, k,
+                                     flags, s.ws, s.ws_bytes, sk);
+            }
             if (rc) return rc;
             CUSTMA_CUDA_CHECK(cudaEventRecord(s.bwd_done, sk));
             CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sout, s.bwd_done, 0));
@@ -340,7 +370,7 @@ int custma_host_wait(uint64_t ticket) {
             if (s.stream) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.stream));
             if (s.d2h) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(s.d2h));
         }
-        for (cudaStream_t st : {c.h2d, c.compute, c.d2h})
+        for (cudaStream_t st : {c.h2d, c.prep, c.compute, c.d2h})
             if (st) CUSTMA_CUDA_CHECK(cudaStreamSynchronize(st));
     }
     return CUSTMA_OK;

@@ -117,12 +117,50 @@ def forward(camera: torch.Tensor, projector: torch.Tensor, D: int = 0, kernel_si
     return cost, best, index
 
 
+class PreparedBackward:
+    """custma_backward_prepare run ahead of time: the workspace that holds the image-dependent half of the backward
+    and the stream it was filled on.  backward(..., prepared=...) waits for that stream and skips the preparation."""
+
+    def __init__(self, ws: torch.Tensor, nbytes: int, stream: "torch.cuda.Stream", key):
+        self.ws, self.nbytes, self.stream, self.key = ws, nbytes, stream, key
+
+
+_prepare_streams = {}
+
+
+def prepare_backward(camera: torch.Tensor, projector: torch.Tensor, kernel_size: int, D: int = 0, *,
+                     flags: int = 0) -> PreparedBackward:
+    """Starts the image-dependent part of backward() (pivots, band copies, window statistics, verdict) on a side stream,
+    so that it runs beside the forward and the loss.  The images must not change until the backward has run."""
+    _check_input(camera, "camera")
+    _check_input(projector, "projector")
+    B, H, W, _ = _shape_bhw(camera, projector)
+    D, k = int(D), int(kernel_size)
+    dev = camera.device
+    with torch.cuda.device(dev):
+        nbytes = binding.backward_workspace_bytes(B, H, W, D, k, flags)
+        if nbytes == 0:
+            binding.check(binding.ERR_INVALID_ARGUMENT, "custma_backward_workspace_bytes")
+        main = torch.cuda.current_stream(dev)
+        side = _prepare_streams.get(dev.index)
+        if side is None:
+            side = _prepare_streams[dev.index] = torch.cuda.Stream(dev)
+        side.wait_stream(main)      # the images are ready, and the workspace is not older work's any more
+        ws, ws_ptr = _workspace(nbytes, dev)
+        binding.backward_prepare(camera.data_ptr(), projector.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes,
+                                 side.cuda_stream)
+        ws.record_stream(side)
+    return PreparedBackward(ws, nbytes, side, (camera.data_ptr(), projector.data_ptr(), B, H, W, D, k, int(flags)))
+
+
 def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: torch.Tensor, kernel_size: int,
-             D: int = 0, *, flags: int = 0, rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+             D: int = 0, *, flags: int = 0, rows: Optional[Tuple[int, int]] = None,
+             prepared: Optional[PreparedBackward] = None) -> torch.Tensor:
     """Gradient of sum(cost * cost_volume_grad) with respect to the camera image; same leading shape as camera.
 
     rows = (row_begin, row_end): the upstream gradient exists only on those volume rows and cost_volume_grad is
-    [..., row_end - row_begin, W, C] (custma_backward_rows: what a row-band shard passes for its owned rows)."""
+    [..., row_end - row_begin, W, C] (custma_backward_rows: what a row-band shard passes for its owned rows).
+    prepared = prepare_backward(camera, projector, ...) of these very images: its half of the work is not repeated."""
     _check_input(cost_volume_grad, "cost_volume_grad")
     _check_input(camera, "camera")
     _check_input(projector, "projector")
@@ -144,14 +182,20 @@ def backward(cost_volume_grad: torch.Tensor, camera: torch.Tensor, projector: to
         nbytes = binding.backward_workspace_bytes(B, H, W, D, k, flags)
         if nbytes == 0:
             binding.check(binding.ERR_INVALID_ARGUMENT, "custma_backward_workspace_bytes")
-        ws, ws_ptr = _workspace(nbytes, camera.device)
+        if prepared is not None:
+            if prepared.key != (camera.data_ptr(), projector.data_ptr(), B, H, W, D, k, int(flags)):
+                raise RuntimeError("prepared belongs to other images, another shape or other flags")
+            torch.cuda.current_stream(camera.device).wait_stream(prepared.stream)
+            ws, ws_ptr, call_flags = prepared.ws, prepared.ws.data_ptr(), flags | binding.FLAG_PREPARED
+        else:
+            (ws, ws_ptr), call_flags = _workspace(nbytes, camera.device), flags
         stream = torch.cuda.current_stream(camera.device).cuda_stream
         if rows is None:
             binding.backward(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
-                             camera_grad.data_ptr(), B, H, W, D, k, flags, ws_ptr, nbytes, stream)
+                             camera_grad.data_ptr(), B, H, W, D, k, call_flags, ws_ptr, nbytes, stream)
         else:
             binding.backward_rows(cost_volume_grad.data_ptr(), camera.data_ptr(), projector.data_ptr(),
-                                  camera_grad.data_ptr(), B, H, W, D, k, r0, r1, flags, ws_ptr, nbytes, stream)
+                                  camera_grad.data_ptr(), B, H, W, D, k, r0, r1, call_flags, ws_ptr, nbytes, stream)
         if ws is not None:
             ws.record_stream(torch.cuda.current_stream(camera.device))
     return camera_grad
@@ -191,6 +235,8 @@ class _CostVolume(torch.autograd.Function):
     def forward(ctx, camera, projector, D, kernel_size, flags):
         ctx.save_for_backward(camera, projector)
         ctx.D, ctx.kernel_size, ctx.flags = int(D), int(kernel_size), int(flags)
+        # the camera gradient's image-dependent half starts now, beside the forward and whatever the loss does
+        ctx.prepared = prepare_backward(camera, projector, kernel_size, D, flags=flags) if camera.requires_grad else None
         cost, _, _ = forward(camera, projector, D, kernel_size, want_cost=True, want_wta=False, flags=flags)
         return cost
 
@@ -198,8 +244,9 @@ class _CostVolume(torch.autograd.Function):
     def backward(ctx, cost_volume_grad):
         camera, projector = ctx.saved_tensors
         cost_volume_grad = cost_volume_grad.contiguous()
-        g = backward(cost_volume_grad, camera, projector, ctx.kernel_size, ctx.D, flags=ctx.flags) \
+        g = backward(cost_volume_grad, camera, projector, ctx.kernel_size, ctx.D, flags=ctx.flags, prepared=ctx.prepared) \
             if ctx.needs_input_grad[0] else None
+        ctx.prepared = None
         gp = backward_projector(cost_volume_grad, camera, projector, ctx.kernel_size, ctx.D) \
             if ctx.needs_input_grad[1] else None
         return g, gp, None, None, None

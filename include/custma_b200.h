@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CUSTMA_ABI_VERSION 2
+#define CUSTMA_ABI_VERSION 3
 
 #define CUSTMA_OK 0
 #define CUSTMA_ERR_INVALID_ARGUMENT 1 /* null pointer, non-positive size, kernel_size out of range, ... */
@@ -64,6 +64,11 @@ extern "C" {
                                  by itself for ill-conditioned (low-texture) inputs.  Needs a banded volume with
                                  D % 4 == 0, D <= 572 (forward) / 540 (backward) and k = 3 or 5;
                                  CUSTMA_ERR_UNSUPPORTED otherwise. */
+
+#define CUSTMA_FLAG_PREPARED 4u /* custma_backward / custma_backward_rows only: `workspace` still holds what
+                                   custma_backward_prepare left there for these very images (same shape, kernel size
+                                   and other flags; nothing else has used the workspace since), so the image-dependent
+                                   preparation is skipped */
 
 int custma_abi_version(void);
 const char *custma_last_error(void);
@@ -109,6 +114,15 @@ int custma_forward_wta(const float *camera, const float *projector, float *cost_
 int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
                     int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* The part of custma_backward that depends on the images only (pivots, band copies, window statistics, conditioning
+ * verdict; the window statistics of the direct kernels), run ahead of time into the backward's workspace: in a training
+ * step the upstream gradient does not exist until the loss has run, but the images do - call this on a second stream
+ * while the forward and the loss run (the forward keeps its own workspace), then custma_backward with
+ * CUSTMA_FLAG_PREPARED on the same workspace once that stream's work is done (event).  Results are bit-identical to
+ * the one-call form.  A no-op where nothing is prepared (CUSTMA_FLAG_TENSOR). */
+int custma_backward_prepare(const float *camera, const float *projector, int32_t B, int32_t H, int32_t W, int32_t D,
+                            int32_t kernel_size, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Backward for an upstream gradient that exists only on volume rows [row_begin, row_end): cost_volume_grad is
  * [B, row_end - row_begin, W, C]; all other rows count as zero.  camera_grad is still [B,H,W] (rows the window cannot

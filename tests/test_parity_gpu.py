@@ -819,6 +819,44 @@ def test_backward_rows_equals_zero_padded_gradient(flags):
         cb.backward(dev(g), dev(cam), dev(proj), k, D, rows=(3, 80))
 
 
+@pytest.mark.parametrize("flags", FLAGS)
+def test_backward_prepared_ahead_of_time_gives_the_same_bits(flags):
+    """custma_backward_prepare on a second stream and workspace while the forward runs, then custma_backward with
+    CUSTMA_FLAG_PREPARED: bit-identical to the one-call backward (sliding-window and direct kernels, and the row window)."""
+    from custereomatching_b200 import binding
+    B, H, W, D, k = 2, 50, 210, 64, 5
+    cam, proj = rand_pair(H, W, seed=31, B=B)
+    cam, proj = dev(cam), dev(proj)
+    g = dev(np.random.RandomState(32).randn(B, H, W, D).astype(np.float32))
+    want = cb.backward(g, cam, proj, k, D, flags=flags)
+    wsb = binding.backward_workspace_bytes(B, H, W, D, k, flags)
+    assert wsb == binding.backward_workspace_bytes(B, H, W, D, k, flags | binding.FLAG_PREPARED)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    side, main = torch.cuda.Stream(), torch.cuda.current_stream()
+    side.wait_stream(main)
+    binding.backward_prepare(cam.data_ptr(), proj.data_ptr(), B, H, W, D, k, flags, ws.data_ptr(), wsb, side.cuda_stream)
+    cost, _, _ = cb.forward(cam, proj, D, k, want_cost=True, want_wta=False, flags=flags)   # meanwhile, on the main stream
+    main.wait_stream(side)
+    got = torch.empty(B, H, W, device="cuda")
+    binding.backward(g.data_ptr(), cam.data_ptr(), proj.data_ptr(), got.data_ptr(), B, H, W, D, k, flags | binding.FLAG_PREPARED,
+                     ws.data_ptr(), wsb, main.cuda_stream)
+    assert torch.equal(got, want)
+    # the same preparation serves a second backward (another gradient, a row window)
+    g2 = dev(np.random.RandomState(33).randn(B, 20, W, D).astype(np.float32))
+    got2 = torch.empty(B, H, W, device="cuda")
+    binding.backward_rows(g2.data_ptr(), cam.data_ptr(), proj.data_ptr(), got2.data_ptr(), B, H, W, D, k, 10, 30,
+                          flags | binding.FLAG_PREPARED, ws.data_ptr(), wsb, main.cuda_stream)
+    assert torch.equal(got2, cb.backward(g2, cam, proj, k, D, flags=flags, rows=(10, 30)))
+    # the host layer: explicit handle, and the autograd function (which prepares during its forward)
+    prep = cb.prepare_backward(cam, proj, k, D, flags=flags)
+    assert torch.equal(cb.backward(g, cam, proj, k, D, flags=flags, prepared=prep), want)
+    with pytest.raises(RuntimeError, match="prepared belongs to"):
+        cb.backward(g, proj, cam, k, D, flags=flags, prepared=prep)
+    cam_req = cam.clone().requires_grad_(True)
+    (cb.cost_volume(cam_req, proj, D, k, flags) * g).sum().backward()
+    assert torch.equal(cam_req.grad, cb.backward(g, cam_req.detach(), proj, k, D, flags=flags))
+
+
 def test_uint8_ingestion():
     rng = np.random.RandomState(3)
     img = rng.randint(0, 256, size=(2, 37, 53, 3)).astype(np.uint8)
