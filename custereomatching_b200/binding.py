@@ -40,6 +40,7 @@ SYMBOLS = (
     "custma_backward",
     "custma_backward_rows",
     "custma_backward_prepare",
+    "custma_forward_prepare",
     "custma_ingest_u8",
     "custma_backward_projector_workspace_bytes",
     "custma_backward_projector",
@@ -86,6 +87,8 @@ def _declare(lib):
                                        _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward.restype = ctypes.c_int
     lib.custma_backward.argtypes = [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
+    lib.custma_forward_prepare.restype = ctypes.c_int
+    lib.custma_forward_prepare.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward_prepare.restype = ctypes.c_int
     lib.custma_backward_prepare.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _u32, _ptr, _size, _ptr]
     lib.custma_backward_rows.restype = ctypes.c_int
@@ -189,6 +192,12 @@ def backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W,
     rc = load().custma_backward_rows(grad_ptr, camera_ptr, projector_ptr, camera_grad_ptr, B, H, W, D, k, row_begin,
                                      row_end, flags, ws_ptr or None, ws_bytes, stream or None)
     check(rc, "custma_backward_rows")
+
+
+def forward_prepare(camera_ptr, projector_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):
+    """The image-dependent part of forward(), ahead of time; then forward(..., flags | FLAG_PREPARED) on the same workspace."""
+    rc = load().custma_forward_prepare(camera_ptr, projector_ptr, B, H, W, D, k, flags, ws_ptr or None, ws_bytes, stream or None)
+    check(rc, "custma_forward_prepare")
 
 
 def backward_prepare(camera_ptr, projector_ptr, B, H, W, D, k, flags, ws_ptr, ws_bytes, stream):

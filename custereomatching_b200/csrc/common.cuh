@@ -127,9 +127,12 @@ bool sliding_forward_supported(const Problem &p);
 bool sliding_backward_supported(const Problem &p);
 size_t sliding_forward_workspace_bytes(const Problem &p);
 size_t sliding_backward_workspace_bytes(const Problem &p);
+// phase: the whole call | only its image-dependent preparation (outputs and gradients unused) | everything after a
+// preparation the workspace still holds (custma_forward_prepare, custma_backward_prepare / CUSTMA_FLAG_PREPARED)
+enum CallPhase { kCallAll = 0, kCallPrepareOnly = 1, kCallPrepared = 2 };
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
                            int32_t *index, const WtaExtras &extras, void *workspace, size_t workspace_bytes,
-                           bool force_tensor, cudaStream_t stream);
+                           bool force_tensor, cudaStream_t stream, CallPhase phase = kCallAll);
 // fused head (sliding_forward.cu): soft disparity * mask, best, index, mask, and the per-pixel state of the backward
 size_t sliding_head_forward_workspace_bytes(const Problem &p);
 int launch_sliding_forward_head(const Problem &p, const float *cam, const float *proj, float *soft_disparity, float *best,
@@ -143,12 +146,9 @@ int launch_sliding_backward_head(const Problem &p, const float *soft_grad, const
 bool tc_forward_supported(const Problem &p);
 int launch_tc_forward(const Problem &p, const float *cam, const float *proj, float *cost, unsigned long long *keys,
                       const uint32_t *fb_count, uint32_t threshold, cudaStream_t stream);
-// phase: the whole call | only its image-dependent preparation (grad and camera_grad unused) | everything after a
-// preparation the workspace still holds (custma_backward_prepare / CUSTMA_FLAG_PREPARED)
-enum BackwardPhase { kBackwardAll = 0, kBackwardPrepareOnly = 1, kBackwardPrepared = 2 };
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
                             float *camera_grad, void *workspace, size_t workspace_bytes, bool force_tensor,
-                            cudaStream_t stream, BackwardPhase phase = kBackwardAll);
+                            cudaStream_t stream, CallPhase phase = kCallAll);
 // tensor-core backward (tc_backward.cu): runs when fb_count is NULL or *fb_count > threshold, then writes camera_grad
 bool tc_backward_supported(const Problem &p);
 size_t tc_backward_scratch_bytes(const Problem &p);

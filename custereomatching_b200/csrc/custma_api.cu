@@ -127,6 +127,7 @@ const char *custma_last_error(void) { return g_error; }
 uint64_t custma_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t custma_forward_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags) {
+    flags &= ~CUSTMA_FLAG_PREPARED;
     Problem p;
     if (make_problem(B, H, W, D, k, &p) != CUSTMA_OK) return 0;
     return forward_ws(p, flags);
@@ -165,12 +166,15 @@ int custma_debug_validate_layout(int32_t B, int32_t H, int32_t W, int32_t D, int
 
 static int forward_impl(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
                         const WtaExtras &extras, int32_t B, int32_t H, int32_t W, int32_t D, int32_t k, uint32_t flags,
-                        void *workspace, size_t workspace_bytes, void *stream_) {
+                        void *workspace, size_t workspace_bytes, void *stream_, bool prepare_only = false) {
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);
     if (rc) return rc;
+    const CallPhase phase = prepare_only ? kCallPrepareOnly : (flags & CUSTMA_FLAG_PREPARED) ? kCallPrepared : kCallAll;
+    flags &= ~CUSTMA_FLAG_PREPARED;
     if (!camera || !projector) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera and projector must not be NULL");
-    if (!cost_volume && !best) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "no output requested (cost_volume and best are both NULL)");
+    if (!prepare_only && !cost_volume && !best)
+        return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "no output requested (cost_volume and best are both NULL)");
     if ((best == nullptr) != (index == nullptr)) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "best and index must be given together");
     if ((extras.mask || extras.masked_disparity) && !best)
         return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "mask / masked_disparity need best and index");
@@ -187,9 +191,12 @@ static int forward_impl(const float *camera, const float *projector, float *cost
         return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 572, k = 3 or 5, and no CUSTMA_FLAG_DIRECT");
     if (use_sliding_fwd(p, flags))
         return launch_sliding_forward(p, camera, projector, cost_volume, best, index, extras, s.rest, s.rest_bytes,
-                                      (flags & CUSTMA_FLAG_TENSOR) != 0, stream);
-    if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
-    if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+                                      (flags & CUSTMA_FLAG_TENSOR) != 0, stream, phase);
+    if (phase != kCallPrepared) {   // the direct kernels' preparation: window means and second moments of both images
+        if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
+        if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
+    }
+    if (phase == kCallPrepareOnly) return CUSTMA_OK;
     if ((rc = launch_direct_forward(p, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2, cost_volume, best, index, stream)))
         return rc;
     return best ? launch_wta_extras(p, best, index, extras, stream) : CUSTMA_OK;
@@ -200,6 +207,12 @@ int custma_forward(const float *camera, const float *projector, float *cost_volu
                    size_t workspace_bytes, void *stream_) {
     return forward_impl(camera, projector, cost_volume, best, index, WtaExtras(), B, H, W, D, k, flags, workspace,
                         workspace_bytes, stream_);
+}
+
+int custma_forward_prepare(const float *camera, const float *projector, int32_t B, int32_t H, int32_t W, int32_t D,
+                           int32_t k, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream_) {
+    return forward_impl(camera, projector, nullptr, nullptr, nullptr, WtaExtras(), B, H, W, D, k, flags & ~CUSTMA_FLAG_PREPARED,
+                        workspace, workspace_bytes, stream_, true);
 }
 
 int custma_forward_wta(const float *camera, const float *projector, float *cost_volume, float *best, int32_t *index,
@@ -217,7 +230,7 @@ static int backward_impl(const float *cost_volume_grad, const float *camera, con
     Problem p;
     int rc = make_problem(B, H, W, D, k, &p);
     if (rc) return rc;
-    const BackwardPhase phase = prepare_only ? kBackwardPrepareOnly : (flags & CUSTMA_FLAG_PREPARED) ? kBackwardPrepared : kBackwardAll;
+    const CallPhase phase = prepare_only ? kCallPrepareOnly : (flags & CUSTMA_FLAG_PREPARED) ? kCallPrepared : kCallAll;
     flags &= ~CUSTMA_FLAG_PREPARED;
     if (prepare_only) {
         if (!camera || !projector) return set_error(CUSTMA_ERR_INVALID_ARGUMENT, "camera and projector must not be NULL");
@@ -239,11 +252,11 @@ static int backward_impl(const float *cost_volume_grad, const float *camera, con
     if (use_sliding_bwd(p, flags))
         return launch_sliding_backward(p, cost_volume_grad, camera, projector, camera_grad, s.rest, s.rest_bytes,
                                        (flags & CUSTMA_FLAG_TENSOR) != 0, stream, phase);
-    if (phase != kBackwardPrepared) {   // the direct kernels' preparation: window means and second moments of both images
+    if (phase != kCallPrepared) {   // the direct kernels' preparation: window means and second moments of both images
         if ((rc = launch_window_stats(camera, B, H, W, k, s.cmean, s.cex2, stream))) return rc;
         if ((rc = launch_window_stats(projector, B, H, W, k, s.pmean, s.pey2, stream))) return rc;
     }
-    if (phase == kBackwardPrepareOnly) return CUSTMA_OK;
+    if (phase == kCallPrepareOnly) return CUSTMA_OK;
     return launch_direct_backward(p, cost_volume_grad, camera, projector, s.cmean, s.cex2, s.pmean, s.pey2,
                                   (float *)s.rest, camera_grad, stream);
 }

@@ -23,7 +23,7 @@ struct Slot {
     cudaStream_t stream = nullptr, d2h = nullptr;   // kernels (+ host->device copies in the per-slot pipeline) | device->host copies
     cudaEvent_t fwd_done = nullptr, bwd_done = nullptr, d2h_done = nullptr;
     cudaEvent_t h2d_done = nullptr, kernels_done = nullptr;   // single-compute-stream pipeline: inputs on the device | inputs free again
-    cudaEvent_t prep_done = nullptr;   // the backward's image-dependent preparation (side stream, under the forward) is in ws_bwd
+    cudaEvent_t fprep_done = nullptr, prep_done = nullptr;   // the image-dependent preparations (side stream) are in ws | in ws_bwd
     void *ws_bwd = nullptr;            // single-compute-stream pipeline: the backward's own workspace
     size_t ws_bwd_bytes = 0;
     float *cam = nullptr, *proj = nullptr, *best = nullptr, *grad = nullptr, *vol = nullptr;
@@ -74,6 +74,7 @@ static void release_locked(HostCtx &g_ctx) {
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernels_done) cudaEventDestroy(s.kernels_done);
         if (s.prep_done) cudaEventDestroy(s.prep_done);
+        if (s.fprep_done) cudaEventDestroy(s.fprep_done);
         cudaFree(s.ws_bwd);
         cudaFree(s.cam); cudaFree(s.proj); cudaFree(s.best); cudaFree(s.grad); cudaFree(s.vol); cudaFree(s.index);
         cudaFree(s.ws); cudaFree(s.u8);
@@ -136,6 +137,7 @@ static int build_ctx(HostCtx &g_ctx, int32_t chunk, int32_t H, int32_t W, int32_
             CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.kernels_done, cudaEventDisableTiming));
             if (g_ctx.prep) {
                 CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.prep_done, cudaEventDisableTiming));
+                CUSTMA_CUDA_CHECK(cudaEventCreateWithFlags(&s.fprep_done, cudaEventDisableTiming));
                 s.ws_bwd_bytes = custma_backward_workspace_bytes(chunk, H, W, D, k, flags);
                 CUSTMA_CUDA_CHECK(cudaMalloc(&s.ws_bwd, std::max<size_t>(s.ws_bwd_bytes, 256)));
             }
@@ -284,17 +286,24 @@ static int submit(const HostImages &img, float *h_best, int32_t *h_index,
             if ((rc = custma_ingest_u8(dc, s.cam, nb, H, W, img.cam_channels, img.cam_channel, img.scale, sk))) return rc;
             if ((rc = custma_ingest_u8(dp, s.proj, nb, H, W, img.proj_channels, img.proj_channel, img.scale, sk))) return rc;
         }
-        // the backward's preparation needs the images only: it runs beside the forward on the lowest-priority stream
-        // (its blocks take what the forward's last wave leaves idle) into the backward's own workspace
-        const bool prepare = g_ctx.single && g_ctx.prep && cost_volume_grad_dev && !img.u8;
+        // The preparations of the forward and of the backward need the images only: they run on the lowest-priority
+        // stream as soon as the chunk's images are on the device - beside the previous chunk's kernels, whose grids
+        // leave their last waves mostly idle - each into its own workspace.
+        const bool prepare = g_ctx.single && g_ctx.prep && !img.u8;
         if (prepare) {
             CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(g_ctx.prep, s.h2d_done, 0));
-            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(g_ctx.prep, s.kernels_done, 0));   // ws_bwd's previous user
-            if ((rc = custma_backward_prepare(s.cam, s.proj, nb, H, W, D, k, flags, s.ws_bwd, s.ws_bwd_bytes, g_ctx.prep))) return rc;
-            CUSTMA_CUDA_CHECK(cudaEventRecord(s.prep_done, g_ctx.prep));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(g_ctx.prep, s.kernels_done, 0));   // the workspaces' previous user
+            if ((rc = custma_forward_prepare(s.cam, s.proj, nb, H, W, D, k, flags, s.ws, s.ws_bytes, g_ctx.prep))) return rc;
+            CUSTMA_CUDA_CHECK(cudaEventRecord(s.fprep_done, g_ctx.prep));
+            CUSTMA_CUDA_CHECK(cudaStreamWaitEvent(sk, s.fprep_done, 0));
+            if (cost_volume_grad_dev) {
+                if ((rc = custma_backward_prepare(s.cam, s.proj, nb, H, W, D, k, flags, s.ws_bwd, s.ws_bwd_bytes, g_ctx.prep))) return rc;
+                CUSTMA_CUDA_CHECK(cudaEventRecord(s.prep_done, g_ctx.prep));
+            }
         }
         float *vol = cost_volume_dev ? cost_volume_dev + (size_t)b0 * pix * C : s.vol;
-        rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags, s.ws, s.ws_bytes, sk);
+        rc = custma_forward(s.cam, s.proj, vol, s.best, s.index, nb, H, W, D, k, flags | (prepare ? CUSTMA_FLAG_PREPARED : 0u),
+                            s.ws, s.ws_bytes, sk);
         if (rc) return rc;
         // results leave on a copy stream, so the backward kernels do not queue behind the copies
         CUSTMA_CUDA_CHECK(cudaEventRecord(s.fwd_done, sk));

@@ -673,7 +673,7 @@ size_t sliding_backward_workspace_bytes(const Problem &p) {
 
 int launch_sliding_backward(const Problem &p, const float *grad, const float *cam, const float *proj,
                             float *camera_grad, void *workspace, size_t workspace_bytes, bool force_tensor,
-                            cudaStream_t stream, BackwardPhase phase) {
+                            cudaStream_t stream, CallPhase phase) {
     SlidingConfig cfg;
     if (!sliding_pick_config(p, true, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
@@ -688,11 +688,11 @@ int launch_sliding_backward(const Problem &p, const float *grad, const float *ca
     if (force_tensor) {
         if (!tc_backward_supported(p))
             return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 540 and k = 3 or 5");
-        if (phase == kBackwardPrepareOnly) return CUSTMA_OK;   // the forced tensor-core kernels prepare nothing
+        if (phase == kCallPrepareOnly) return CUSTMA_OK;   // the forced tensor-core kernels prepare nothing
         return launch_tc_backward(p, grad, cam, proj, camera_grad, tc_scratch, nullptr, 0, stream);
     }
-    int rc = phase == kBackwardPrepared ? CUSTMA_OK : launch_sliding_prep(p, L, cam, proj, ws, stream);
-    if (rc || phase == kBackwardPrepareOnly) return rc;
+    int rc = phase == kCallPrepared ? CUSTMA_OK : launch_sliding_prep(p, L, cam, proj, ws, stream);
+    if (rc || phase == kCallPrepareOnly) return rc;
     // same cross-over as the forward (sliding_forward.cu): above this share of flagged work the tensor-core kernel
     // computes the whole call and the sliding / fallback / finalize kernels return at once
     const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;

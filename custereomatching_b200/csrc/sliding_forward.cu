@@ -392,7 +392,7 @@ constexpr double kTensorShare = 0.04;
 
 int launch_sliding_forward(const Problem &p, const float *cam, const float *proj, float *cost, float *best,
                            int32_t *index, const WtaExtras &extras, void *workspace, size_t workspace_bytes,
-                           bool force_tensor, cudaStream_t stream) {
+                           bool force_tensor, cudaStream_t stream, CallPhase phase) {
     SlidingConfig cfg;
     if (!sliding_pick_config(p, false, &cfg)) return set_error(CUSTMA_ERR_UNSUPPORTED, "no sliding-window kernel for k=%d", p.k);
     SlidingLayout L;
@@ -405,9 +405,11 @@ int launch_sliding_forward(const Problem &p, const float *cam, const float *proj
     if (force_tensor) {
         if (!tc_forward_supported(p))
             return set_error(CUSTMA_ERR_UNSUPPORTED, "CUSTMA_FLAG_TENSOR needs a banded volume with D %% 4 == 0, D <= 572 and k = 3 or 5");
+        if (phase == kCallPrepareOnly) return CUSTMA_OK;   // the forced tensor-core kernels prepare nothing
         if ((rc = launch_tc_forward(p, cam, proj, cost, keys, nullptr, 0, stream))) return rc;   // writes every key itself
     } else {
-        if ((rc = launch_sliding_prep(p, L, cam, proj, ws, stream))) return rc;
+        if (phase != kCallPrepared && (rc = launch_sliding_prep(p, L, cam, proj, ws, stream))) return rc;
+        if (phase == kCallPrepareOnly) return CUSTMA_OK;
         const double items = (double)p.B * L.NB * L.n_wtiles * L.fb_groups;
         const uint32_t thr = tc_forward_supported(p) ? (uint32_t)(kTensorShare * items) : 0xffffffffu;
         rc = p.k == 3 ? launch_k<3>(cfg, p, L, ws, cost, keys, thr, HeadOut(), stream)

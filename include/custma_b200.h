@@ -65,10 +65,10 @@ extern "C" {
                                  D % 4 == 0, D <= 572 (forward) / 540 (backward) and k = 3 or 5;
                                  CUSTMA_ERR_UNSUPPORTED otherwise. */
 
-#define CUSTMA_FLAG_PREPARED 4u /* custma_backward / custma_backward_rows only: `workspace` still holds what
-                                   custma_backward_prepare left there for these very images (same shape, kernel size
-                                   and other flags; nothing else has used the workspace since), so the image-dependent
-                                   preparation is skipped */
+#define CUSTMA_FLAG_PREPARED 4u /* custma_forward / custma_forward_wta / custma_backward / custma_backward_rows:
+                                   `workspace` still holds what custma_forward_prepare (custma_backward_prepare) left
+                                   there for these very images (same shape, kernel size and other flags; nothing else
+                                   has used the workspace since), so the image-dependent preparation is skipped */
 
 int custma_abi_version(void);
 const char *custma_last_error(void);
@@ -114,6 +114,11 @@ int custma_forward_wta(const float *camera, const float *projector, float *cost_
 int custma_backward(const float *cost_volume_grad, const float *camera, const float *projector, float *camera_grad,
                     int32_t B, int32_t H, int32_t W, int32_t D, int32_t kernel_size, uint32_t flags, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* The part of custma_forward / custma_forward_wta that depends on the images only (see custma_backward_prepare below):
+ * a pipeline that streams batches runs it for batch i+1 beside the kernels of batch i. */
+int custma_forward_prepare(const float *camera, const float *projector, int32_t B, int32_t H, int32_t W, int32_t D,
+                           int32_t kernel_size, uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
 
 /* The part of custma_backward that depends on the images only (pivots, band copies, window statistics, conditioning
  * verdict; the window statistics of the direct kernels), run ahead of time into the backward's workspace: in a training

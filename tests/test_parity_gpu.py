@@ -847,6 +847,17 @@ def test_backward_prepared_ahead_of_time_gives_the_same_bits(flags):
     binding.backward_rows(g2.data_ptr(), cam.data_ptr(), proj.data_ptr(), got2.data_ptr(), B, H, W, D, k, 10, 30,
                           flags | binding.FLAG_PREPARED, ws.data_ptr(), wsb, main.cuda_stream)
     assert torch.equal(got2, cb.backward(g2, cam, proj, k, D, flags=flags, rows=(10, 30)))
+    # the forward's counterpart: custma_forward_prepare + CUSTMA_FLAG_PREPARED, cost and WTA
+    cost0, best0, disp0 = cb.forward(cam, proj, D, k, want_cost=True, want_wta=True, flags=flags)
+    wsf_b = binding.forward_workspace_bytes(B, H, W, D, k, flags)
+    wsf = torch.empty(wsf_b, dtype=torch.uint8, device="cuda")
+    side.wait_stream(main)
+    binding.forward_prepare(cam.data_ptr(), proj.data_ptr(), B, H, W, D, k, flags, wsf.data_ptr(), wsf_b, side.cuda_stream)
+    main.wait_stream(side)
+    cost1, best1, disp1 = torch.empty_like(cost0), torch.empty_like(best0), torch.empty_like(disp0)
+    binding.forward(cam.data_ptr(), proj.data_ptr(), cost1.data_ptr(), best1.data_ptr(), disp1.data_ptr(), B, H, W, D, k,
+                    flags | binding.FLAG_PREPARED, wsf.data_ptr(), wsf_b, main.cuda_stream)
+    assert torch.equal(cost1, cost0) and torch.equal(best1, best0) and torch.equal(disp1, disp0)
     # the host layer: explicit handle, and the autograd function (which prepares during its forward)
     prep = cb.prepare_backward(cam, proj, k, D, flags=flags)
     assert torch.equal(cb.backward(g, cam, proj, k, D, flags=flags, prepared=prep), want)
