@@ -765,21 +765,35 @@ def bench_cfg5(args, rank, local, world, device):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     gather_res = ResultGather((2, max_hc, W), torch.float32, device, rank, world, args.gather)
     gather_grad = ResultGather((max_hc, W), torch.float32, device, rank, world, args.gather)
-    stream = torch.cuda.current_stream(device)
+    # as in bench_batch: the step on a high-priority stream, the backward's preparation beside the forward
+    prepare = not args.no_prepare
+    torch.cuda.synchronize(device)
+    stream = torch.cuda.Stream(device, priority=-1) if prepare else torch.cuda.current_stream(device)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    ws_bwd_bytes = binding.backward_workspace_bytes(1, Hc, W, D, k, 0)
+    ws_bwd = torch.empty(ws_bwd_bytes, dtype=torch.uint8, device=device) if prepare else None
+    prep_stream = torch.cuda.Stream(device) if prepare else None
 
     def fwd():
         binding.forward(cam.data_ptr(), proj.data_ptr(), cost.data_ptr(), best.data_ptr(), disp.data_ptr(), 1, Hc, W, D, k, 0,
                         ws.data_ptr(), ws_bytes, sptr)
 
-    def bwd():
+    def bwd(prepared=False):
         binding.backward_rows(grad_in.data_ptr(), cam.data_ptr(), proj.data_ptr(), cam_grad.data_ptr(), 1, Hc, W, D, k,
-                              b0, b1, 0, ws.data_ptr(), ws_bytes, sptr)
+                              b0, b1, binding.FLAG_PREPARED if prepared else 0,
+                              (ws_bwd if prepared else ws).data_ptr(), ws_bwd_bytes if prepared else ws_bytes, sptr)
 
     def step():
+        if prepare:
+            prep_stream.wait_stream(stream)
+            binding.backward_prepare(cam.data_ptr(), proj.data_ptr(), 1, Hc, W, D, k, 0, ws_bwd.data_ptr(), ws_bwd_bytes,
+                                     prep_stream.cuda_stream)
         fwd()
         p1 = gather_res.start(results, stream)
-        bwd()
+        if prepare:
+            stream.wait_stream(prep_stream)
+        bwd(prepare)
         p2 = gather_grad.start(cam_grad, stream)
         gather_res.wait(p1, stream)
         gather_grad.wait(p2, stream)

@@ -171,11 +171,14 @@ def batch_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int, ke
     Returns (best, disparity, camera_grad | None), gathered over ranks to the full batch when gather=True."""
     from . import functional as F
     rank, world = _world(group)
+    # the backward's image-dependent half runs on a side stream beside the forward and the loss
+    extra = {"prepared": F.prepare_backward(camera, projector, kernel_size, D)} \
+        if cost_volume_grad_fn is not None and camera.is_cuda else {}
     cost, best, disp = F.forward(camera, projector, D, kernel_size, want_cost=cost_volume_grad_fn is not None,
                                  want_wta=True)
     grad = None
     if cost_volume_grad_fn is not None:
-        grad = F.backward(cost_volume_grad_fn(cost), camera, projector, kernel_size, D)
+        grad = F.backward(cost_volume_grad_fn(cost), camera, projector, kernel_size, D, **extra)
     if gather and world > 1:
         B = int(global_batch) if global_batch is not None else sum(_gather_sizes(camera.shape[0], group))
         best = all_gather_batch(best, B, group)
@@ -208,6 +211,8 @@ def row_band_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int,
     band = row_band(H, kernel_size, rank, world)
     cam_c = crop_rows_with_halo(camera, band)
     proj_c = crop_rows_with_halo(projector, band)
+    extra = {"prepared": F.prepare_backward(cam_c, proj_c, kernel_size, D)} \
+        if cost_volume_grad_fn is not None and cam_c.is_cuda else {}
     cost, best, disp = F.forward(cam_c, proj_c, D, kernel_size, want_cost=cost_volume_grad_fn is not None,
                                  want_wta=True)
     grad = None
@@ -215,7 +220,7 @@ def row_band_sharded_step(camera: torch.Tensor, projector: torch.Tensor, D: int,
         # gradient of the OWNED rows only, handed over as it is: custma_backward_rows treats the halo rows of the crop as
         # zero, so no volume-sized zero fill or copy happens here
         g = cost_volume_grad_fn(band_rows_of(cost, band), band)
-        grad = F.backward(g.contiguous(), cam_c, proj_c, kernel_size, D, rows=band_gradient_mask_rows(band))
+        grad = F.backward(g.contiguous(), cam_c, proj_c, kernel_size, D, rows=band_gradient_mask_rows(band), **extra)
         grad = assemble_row_band_gradient(grad, H, kernel_size, group)
     best = all_gather_row_bands(band_rows_of(best, band), H, kernel_size, group)
     disp = all_gather_row_bands(band_rows_of(disp, band), H, kernel_size, group)
