@@ -480,7 +480,7 @@ def bench_batch(args, rank, local, world, device):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     # the backward's image-dependent preparation runs on a second stream beside the forward, into its own workspace
     # (custma_backward_prepare / CUSTMA_FLAG_PREPARED; --no-prepare: the plain two calls)
-    prepare = not args.no_prepare
+    prepare = not args.no_prepare and P * H * W * C >= 32e6    # below that the second stream's events cost more than they hide
     ws_bwd_bytes = binding.backward_workspace_bytes(P, H, W, D, k, flags)
     ws_bwd = torch.empty(max(ws_bwd_bytes, 256), dtype=torch.uint8, device=device) if prepare else None
     prep_stream = torch.cuda.Stream(device) if prepare else None

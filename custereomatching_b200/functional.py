@@ -236,7 +236,10 @@ class _CostVolume(torch.autograd.Function):
         ctx.save_for_backward(camera, projector)
         ctx.D, ctx.kernel_size, ctx.flags = int(D), int(kernel_size), int(flags)
         # the camera gradient's image-dependent half starts now, beside the forward and whatever the loss does
-        ctx.prepared = prepare_backward(camera, projector, kernel_size, D, flags=flags) if camera.requires_grad else None
+        # (not for tiny volumes: below ~32 Mcell the second stream's events cost more than they hide)
+        C = int(D) if int(D) > 0 else camera.shape[-1]
+        ctx.prepared = prepare_backward(camera, projector, kernel_size, D, flags=flags) \
+            if camera.requires_grad and camera.numel() * C >= 32e6 else None
         cost, _, _ = forward(camera, projector, D, kernel_size, want_cost=True, want_wta=False, flags=flags)
         return cost
 

@@ -868,6 +868,19 @@ def test_backward_prepared_ahead_of_time_gives_the_same_bits(flags):
     assert torch.equal(cam_req.grad, cb.backward(g, cam_req.detach(), proj, k, D, flags=flags))
 
 
+def test_autograd_prepares_the_backward_of_large_volumes():
+    """From 32 Mcell on the autograd function starts the backward's preparation during its forward; same bits."""
+    H, W, D, k = 160, 640, 320, 5
+    cam, proj = rand_pair(H, W, seed=41)
+    cam, proj = dev(cam), dev(proj)
+    cam_req = cam.clone().requires_grad_(True)
+    cost = cb.cost_volume(cam_req, proj, D, k)
+    assert cost.grad_fn.prepared is not None
+    g = torch.randn(H, W, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    (cost * g).sum().backward()
+    assert torch.equal(cam_req.grad, cb.backward(g, cam, proj, k, D))
+
+
 def test_uint8_ingestion():
     rng = np.random.RandomState(3)
     img = rng.randint(0, 256, size=(2, 37, 53, 3)).astype(np.uint8)
