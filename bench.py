@@ -691,7 +691,9 @@ def bench_batch(args, rank, local, world, device):
                "d2h_bytes_per_step": 3 * P * pix * 4, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
                "api": "custma_host_submit / custma_host_wait (include/custma_b200.h; custma_host_step = both): pinned host "
                       "images in, host best/disparity/camera_grad out every step, results of step i-1 awaited after "
-                      "step i is submitted; upstream gradient produced on the device; volume in the library's per-slot buffer"}
+                      "step i is submitted; upstream gradient produced on the device; volume in the library's per-slot buffer; "
+                      "copies in / kernels / copies out on three streams, the image-dependent preparations of a step "
+                      "beside the previous step's kernels"}
         # parity of the two paths on this very data (cheap sanity, outside the timed regions)
         same = bool(torch.equal(h_best.to(device), best) and torch.equal(h_grad.to(device), cam_grad))
         e2e["matches_device_path"] = same
