@@ -670,7 +670,7 @@ def bench_batch(args, rank, local, world, device):
 
         for i in range(3):
             binding.host_wait(host_submit(i))
-        Ke = max(3, K)
+        Ke = max(30, K)   # enough steps that filling and draining the pipeline (one copy in, one copy out) does not show
         barrier()
         t0 = time.perf_counter()
         prev = None
